@@ -1,0 +1,850 @@
+// =============================================================================
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.  Nothing under cuopt_b200/ includes,
+// links or loads this file; only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / `--impl reference` leg use it (through oracle/pdlp_oracle.py).
+//
+// CPU restatement (fp64, sequential summation order) of the reference's PDLP
+// as NVIDIA/cuopt 25.08 runs it on the GPU.  The reference's own GPU
+// implementation cannot be built offline (RAFT/RMM/rapids-cmake are fetched
+// from the network), and its SpMV / dot / nrm2 arithmetic executes inside
+// closed-source cuSPARSE (cusparseSpMV, CUSPARSE_SPMV_CSR_ALG2) and cuBLAS
+// (cublasDdot / cublasDnrm2) of the CUDA 12.9 toolkit, so this file restates
+// the published algorithm at the reference's call sites.  Each function cites
+// the reference lines it follows (paths relative to
+// /root/reference/cpp/src/linear_programming unless noted).
+//
+// PINNED against the reference's own known answers (tests/test_oracle_pins.py):
+//   * afiro Methodical1 initial step size 1.4893 / primal weight 0.0141652 +-1e-4
+//       (cpp/tests/linear_programming/pdlp_test.cu:237-283)
+//   * afiro default-settings primal vector, 32 values, rel 1e-4
+//       (python/cuopt/cuopt/tests/linear_programming/test_lp_solver.py:430-476)
+//   * afiro objective -464.7531 (rel 1e-6) (test_lp_solver.py:101-121, :592-606)
+//   * good-max 17.0, max_offset 0.0 +-1e-4 (pdlp_test.cu:909-943); ranged C-API LP 32.0
+//       (c_api_tests/c_api_test.c:761-874)
+//   * objectives of the reference's CPU dual simplex (oracle/_ref) on every on-disk instance
+// NOT pinned by any reference test: absolute iteration counts.
+//
+// Summation order: row sums of the SpMVs run left to right in CSR order; vector
+// reductions are chunked (4096 elements per chunk, chunks added left to right),
+// which makes results independent of the OpenMP thread count.
+// Trust-region restart (Methodical1's restart rule, pdlp_restart_strategy.cu:278-364,
+// 983-1678) is not restated: the oracle covers restart_strategy 0 (none) and 1 (KKT),
+// i.e. the Stable1 / Stable2 / Fast1 presets; Methodical1 is covered up to its
+// initial scaling / step size / primal weight (what the reference test pins).
+// =============================================================================
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr double kInf = std::numeric_limits<double>::infinity();
+
+struct hyper_t {  // pdlp_hyper_params.cu:22-80, field order is the ctypes ABI (oracle/pdlp_oracle.py)
+  double initial_step_size_scaling;
+  int l_inf_ruiz_iterations;
+  int do_pock_chambolle_scaling;
+  int do_ruiz_scaling;
+  double alpha_pock_chambolle;
+  double artificial_restart_threshold;
+  int compute_initial_step_size_before_scaling;
+  int compute_initial_primal_weight_before_scaling;
+  double initial_primal_weight_c_scaling;
+  double initial_primal_weight_b_scaling;
+  int major_iteration;
+  int min_iteration_restart;
+  int restart_strategy;
+  int never_restart_to_average;
+  double reduction_exponent;
+  double growth_exponent;
+  double primal_weight_update_smoothing;
+  double sufficient_reduction_for_restart;
+  double necessary_reduction_for_restart;
+  double primal_importance;
+  double primal_distance_smoothing;
+  double dual_distance_smoothing;
+  int compute_last_restart_before_new_primal_weight;
+  int artificial_restart_in_main_loop;
+  int rescale_for_restart;
+  int handle_some_primal_gradients_on_finite_bounds_as_residuals;
+  int project_initial_primal;
+};
+
+struct settings_t {
+  double abs_dual_tol, rel_dual_tol, abs_primal_tol, rel_primal_tol, abs_gap_tol, rel_gap_tol;
+  int iteration_limit;
+  double time_limit;
+  int num_threads;
+};
+
+struct stats_t {
+  int termination_status;  // constants.h:62-72
+  int number_of_steps_taken;
+  int total_number_of_attempted_steps;
+  double primal_objective, dual_objective, gap, relative_gap;
+  double l2_primal_residual, l2_relative_primal_residual;
+  double l2_dual_residual, l2_relative_dual_residual;
+  double step_size, primal_weight;
+  int n_restarts, n_major;
+  double solve_seconds;
+  int solution_is_average;
+};
+
+struct csr_t {
+  int rows = 0, cols = 0;
+  std::vector<int> off, idx;
+  std::vector<double> val;
+};
+
+// y = A x, each row summed left to right (what a one-thread-per-row CSR kernel does).
+void spmv(const csr_t& A, const double* x, double* y)
+{
+#pragma omp parallel for schedule(static) if (A.rows > 20000)
+  for (int i = 0; i < A.rows; ++i) {
+    double s = 0.0;
+    for (int p = A.off[i]; p < A.off[i + 1]; ++p)
+      s += A.val[p] * x[A.idx[p]];
+    y[i] = s;
+  }
+}
+
+// Chunked deterministic reduction of f(i) over [0,n).
+template <typename F>
+double reduce_sum(int n, F f)
+{
+  constexpr int CH = 4096;
+  const int nch    = (n + CH - 1) / CH;
+  std::vector<double> part(std::max(nch, 1), 0.0);
+#pragma omp parallel for schedule(static) if (nch > 8)
+  for (int c = 0; c < nch; ++c) {
+    double s     = 0.0;
+    const int hi = std::min(n, (c + 1) * CH);
+    for (int i = c * CH; i < hi; ++i)
+      s += f(i);
+    part[c] = s;
+  }
+  double s = 0.0;
+  for (int c = 0; c < nch; ++c)
+    s += part[c];
+  return s;
+}
+
+// CSR transpose with stable (row-ascending) order inside each transposed row, the order
+// cusparseCsr2cscEx2 produces (reference: mip/problem/problem.cu:277-309).
+csr_t transpose(const csr_t& A)
+{
+  csr_t T;
+  T.rows = A.cols;
+  T.cols = A.rows;
+  T.off.assign(A.cols + 1, 0);
+  T.idx.resize(A.idx.size());
+  T.val.resize(A.val.size());
+  for (int j : A.idx)
+    T.off[j + 1]++;
+  for (int j = 0; j < A.cols; ++j)
+    T.off[j + 1] += T.off[j];
+  std::vector<int> cur(T.off.begin(), T.off.end() - 1);
+  for (int i = 0; i < A.rows; ++i)
+    for (int p = A.off[i]; p < A.off[i + 1]; ++p) {
+      const int q = cur[A.idx[p]]++;
+      T.idx[q]    = i;
+      T.val[q]    = A.val[p];
+    }
+  return T;
+}
+
+// utils.cuh:140-148
+inline double combine_finite_abs_bounds(double lower, double upper)
+{
+  double v = 0.0;
+  if (std::isfinite(upper)) v = std::max(v, std::fabs(upper));
+  if (std::isfinite(lower)) v = std::max(v, std::fabs(lower));
+  return v;
+}
+// utils.cuh:166-178
+inline double violation(double value, double lower, double upper)
+{
+  if (value < lower) return lower - value;
+  if (value > upper) return value - upper;
+  return 0.0;
+}
+// utils.cuh:205-219
+inline double bound_value_reduced_cost_product(double value, double lower, double upper)
+{
+  double bound_value = 0.0;
+  if (value > 0.0)
+    bound_value = lower;
+  else if (value < 0.0)
+    bound_value = upper;
+  return std::isfinite(bound_value) ? value * bound_value : 0.0;
+}
+// raft::linalg::eltwiseDivideCheckZero: a / b, 0 when b == 0
+inline double div_check_zero(double a, double b) { return b == 0.0 ? 0.0 : a / b; }
+
+struct convergence_t {  // termination_strategy/convergence_information.cu
+  double l2_primal_residual = 0, l2_dual_residual = 0, primal_objective = 0, dual_objective = 0;
+  double gap = 0, abs_objective = 0, l2_primal_variable = 0, l2_dual_variable = 0;
+  std::vector<double> reduced_cost;
+  int status = 6;
+};
+
+struct trace_row_t {
+  int k, restarted, to_average;
+  double primal_objective, dual_objective, gap, l2_primal_residual, l2_dual_residual, step_size, primal_weight,
+    kkt_current, kkt_average;
+};
+
+class oracle_t {
+ public:
+  // ---- unscaled problem after problem_t construction (mip/problem/problem.cu:55-93) ----
+  int m, n;
+  csr_t A, AT;
+  std::vector<double> c, l, u, lc, uc, b_comb;
+  double obj_scale, obj_offset;  // objective = obj_scale * c'x + obj_offset  (c already negated when maximising)
+  bool maximize;
+  hyper_t hp;
+  settings_t st;
+
+  // ---- scaled problem (initial_scaling.cu) ----
+  csr_t As, ATs;
+  std::vector<double> cs, ls, us, lcs, ucs;
+  std::vector<double> Dr, Dc;  // cumulative constraint / variable scaling
+
+  // ---- iterate state (saddle_point.cu:26-60: x = y = 0) ----
+  std::vector<double> x, y, xn, yn, xbar, dx, dy, AtY, AtYn, Ax;
+  std::vector<double> sum_x, sum_y, x_avg, y_avg, x_lr, y_lr, tmp_n, tmp_m;
+  double sum_w             = 0.0;
+  double step_size         = 0.0, primal_weight = 0.0, tau = 0.0, sigma = 0.0;
+  double interaction = 0, norm_dx2 = 0, norm_dy2 = 0;
+  int k_total = 0, k_internal = 0, k_pdhg_host = 0, k_pdhg_dev = 0, its_since_restart = 0;
+  bool last_restart_was_average = false;
+  int valid_step_size           = 0;
+  double last_candidate_kkt = 0.0, last_restart_kkt = 0.0;
+  double l2_norm_c = 0.0, l2_norm_b = 0.0;
+  convergence_t conv_cur, conv_avg;
+  bool initialised = false;
+  int n_restarts = 0, n_major = 0;
+  std::vector<trace_row_t> trace;
+  stats_t result{};
+  std::vector<double> sol_x, sol_y, sol_rc;
+
+  oracle_t(int m_, int n_, const int* off, const int* idx, const double* val, const double* c_, const double* l_,
+           const double* u_, const double* lc_, const double* uc_, int maximize_, double offset, const hyper_t& h,
+           const settings_t& s)
+    : m(m_), n(n_), hp(h), st(s)
+  {
+    A.rows = m;
+    A.cols = n;
+    A.off.assign(off, off + m + 1);
+    A.idx.assign(idx, idx + off[m]);
+    A.val.assign(val, val + off[m]);
+    c.assign(c_, c_ + n);
+    l.assign(l_, l_ + n);
+    u.assign(u_, u_ + n);
+    lc.assign(lc_, lc_ + m);
+    uc.assign(uc_, uc_ + m);
+    maximize   = maximize_ != 0;
+    obj_scale  = 1.0;
+    obj_offset = offset;
+    // mip/problem/problem_helpers.cuh:128-142: maximise => negate c, flip the objective scaling factor
+    if (maximize) {
+      for (auto& v : c)
+        v = -v;
+      obj_scale = -obj_scale;
+    }
+    AT = transpose(A);
+    b_comb.resize(m);
+    for (int i = 0; i < m; ++i)
+      b_comb[i] = combine_finite_abs_bounds(lc[i], uc[i]);
+    // convergence_information.cu:74-82: norms of the UNSCALED c and combined bounds (cublasDnrm2)
+    l2_norm_c = std::sqrt(reduce_sum(n, [&](int j) { return c[j] * c[j]; }));
+    l2_norm_b = std::sqrt(reduce_sum(m, [&](int i) { return b_comb[i] * b_comb[i]; }));
+  }
+
+  // ------------------------------------------------------------------ scaling
+  // initial_scaling.cu:85-163 (Ruiz, L-inf), :177-307 (Pock-Chambolle)
+  void compute_scaling_vectors()
+  {
+    Dr.assign(m, 1.0);
+    Dc.assign(n, 1.0);
+    std::vector<double> it_r(m), it_c(n);
+    auto bounded_div_sqrt = [](double a, double b) { return b > 0.0 ? a / std::sqrt(b) : a; };  // utils.cuh:123-129
+    if (hp.do_ruiz_scaling) {
+      for (int it = 0; it < hp.l_inf_ruiz_iterations; ++it) {
+        std::fill(it_r.begin(), it_r.end(), 0.0);
+        std::fill(it_c.begin(), it_c.end(), 0.0);
+        for (int i = 0; i < m; ++i)
+          for (int p = A.off[i]; p < A.off[i + 1]; ++p) {
+            const int j    = A.idx[p];
+            const double a = std::fabs((A.val[p] * Dr[i]) * Dc[j]);  // :104-106
+            it_r[i]        = std::max(it_r[i], a);
+            it_c[j]        = std::max(it_c[j], a);
+          }
+        for (int i = 0; i < m; ++i)
+          Dr[i] = bounded_div_sqrt(Dr[i], it_r[i]);
+        for (int j = 0; j < n; ++j)
+          Dc[j] = bounded_div_sqrt(Dc[j], it_c[j]);
+      }
+    }
+    if (hp.do_pock_chambolle_scaling) {
+      const double alpha = hp.alpha_pock_chambolle;
+      for (int i = 0; i < m; ++i) {  // :177-213 rows of A
+        double s = 0.0;
+        for (int p = A.off[i]; p < A.off[i + 1]; ++p)
+          s += std::pow(std::fabs((A.val[p] * Dr[i]) * Dc[A.idx[p]]), alpha);
+        it_r[i] = s;
+      }
+      for (int j = 0; j < n; ++j) {  // :216-252 rows of A^T, same association (a*Dr)*Dc
+        double s = 0.0;
+        for (int p = AT.off[j]; p < AT.off[j + 1]; ++p)
+          s += std::pow(std::fabs((AT.val[p] * Dr[AT.idx[p]]) * Dc[j]), 2.0 - alpha);
+        it_c[j] = s;
+      }
+      for (int i = 0; i < m; ++i)
+        Dr[i] = bounded_div_sqrt(Dr[i], it_r[i]);
+      for (int j = 0; j < n; ++j)
+        Dc[j] = bounded_div_sqrt(Dc[j], it_c[j]);
+    }
+  }
+
+  // initial_scaling.cu:310-408
+  void scale_problem()
+  {
+    As  = A;
+    ATs = AT;
+    for (int i = 0; i < m; ++i)
+      for (int p = A.off[i]; p < A.off[i + 1]; ++p)
+        As.val[p] = A.val[p] * Dr[i] * Dc[A.idx[p]];  // :310-326
+    for (int j = 0; j < n; ++j)
+      for (int p = AT.off[j]; p < AT.off[j + 1]; ++p)
+        ATs.val[p] = AT.val[p] * Dc[j] * Dr[AT.idx[p]];  // :329-345 (note the other association order)
+    cs.resize(n); ls.resize(n); us.resize(n); lcs.resize(m); ucs.resize(m);
+    for (int j = 0; j < n; ++j) {
+      cs[j] = c[j] * Dc[j];
+      ls[j] = div_check_zero(l[j], Dc[j]);
+      us[j] = div_check_zero(u[j], Dc[j]);
+    }
+    for (int i = 0; i < m; ++i) {
+      lcs[i] = lc[i] * Dr[i];
+      ucs[i] = uc[i] * Dr[i];
+    }
+    scale_solutions(x, y);  // :404-407
+  }
+  void scale_solutions(std::vector<double>& px, std::vector<double>& py) const  // :411-427
+  {
+    for (int j = 0; j < n; ++j) px[j] = div_check_zero(px[j], Dc[j]);
+    for (int i = 0; i < m; ++i) py[i] = div_check_zero(py[i], Dr[i]);
+  }
+  void unscale_solutions(std::vector<double>& px, std::vector<double>& py) const  // :456-484
+  {
+    for (int j = 0; j < n; ++j) px[j] *= Dc[j];
+    for (int i = 0; i < m; ++i) py[i] *= Dr[i];
+  }
+
+  // pdlp.cu:1225-1258: step = initial_step_size_scaling / max|a_ij| of the matrix `M` currently in op_problem_scaled_
+  void compute_initial_step_size(const csr_t& M)
+  {
+    double mx = 0.0;
+    for (double v : M.val)
+      mx = std::max(mx, std::fabs(v));
+    step_size = div_check_zero(hp.initial_step_size_scaling, mx);
+  }
+  // pdlp.cu:1261-1309
+  void compute_initial_primal_weight(const std::vector<double>& cc, const std::vector<double>& lo,
+                                     const std::vector<double>& hi)
+  {
+    const double bs = hp.initial_primal_weight_b_scaling, csn = hp.initial_primal_weight_c_scaling;
+    const double bn = std::sqrt(reduce_sum(m, [&](int i) {
+      const double v = combine_finite_abs_bounds(lo[i], hi[i]);
+      return v * v * bs;
+    }));
+    const double cn = std::sqrt(reduce_sum(n, [&](int j) { return cc[j] * cc[j] * csn; }));
+    if (bn > 0.0 && cn > 0.0)
+      primal_weight = hp.primal_importance * (cn / bn);
+    else
+      primal_weight = hp.primal_importance;
+  }
+
+  // pdlp.cu:984-1056 up to the start of the while loop
+  void initialise()
+  {
+    x.assign(n, 0.0); y.assign(m, 0.0); xn.assign(n, 0.0); yn.assign(m, 0.0); xbar.assign(n, 0.0);
+    dx.assign(n, 0.0); dy.assign(m, 0.0); AtY.assign(n, 0.0); AtYn.assign(n, 0.0); Ax.assign(m, 0.0);
+    sum_x.assign(n, 0.0); sum_y.assign(m, 0.0); x_avg.assign(n, 0.0); y_avg.assign(m, 0.0);
+    x_lr.assign(n, 0.0); y_lr.assign(m, 0.0); tmp_n.assign(n, 0.0); tmp_m.assign(m, 0.0);
+    conv_cur.reduced_cost.assign(n, 0.0);
+    conv_avg.reduced_cost.assign(n, 0.0);
+    compute_scaling_vectors();  // scaling strategy ctor, initial_scaling.cu:36-83
+    if (hp.compute_initial_step_size_before_scaling) compute_initial_step_size(A);
+    if (hp.compute_initial_primal_weight_before_scaling) compute_initial_primal_weight(c, lc, uc);
+    scale_problem();
+    if (!hp.compute_initial_step_size_before_scaling) compute_initial_step_size(As);
+    if (!hp.compute_initial_primal_weight_before_scaling) compute_initial_primal_weight(cs, lcs, ucs);
+    tau   = step_size / primal_weight;  // adaptive_step_size_strategy.cu:348-366
+    sigma = step_size * primal_weight;
+    if (hp.project_initial_primal) {  // pdlp.cu:1041-1056, clamp = min(max(v, lo), hi) (utils.cuh:131-137)
+      for (int j = 0; j < n; ++j) {
+        x[j]     = std::min(std::max(x[j], ls[j]), us[j]);
+        x_avg[j] = std::min(std::max(x_avg[j], ls[j]), us[j]);
+      }
+    }
+    initialised = true;
+  }
+
+  // --------------------------------------------------------------- PDHG step
+  // pdhg.cu:137-158 + utils.cuh:81-95
+  void primal_projection()
+  {
+#pragma omp parallel for schedule(static) if (n > 20000)
+    for (int j = 0; j < n; ++j) {
+      const double gradient = cs[j] - AtY[j];
+      double next           = x[j] - (tau * gradient);
+      next                  = std::max(std::min(next, us[j]), ls[j]);
+      xn[j]                 = next;
+      dx[j]                 = next - x[j];
+      xbar[j]               = next - x[j] + next;
+    }
+  }
+  // pdhg.cu:73-117 + utils.cuh:98-112
+  void dual_projection()
+  {
+    spmv(As, xbar.data(), Ax.data());
+#pragma omp parallel for schedule(static) if (m > 20000)
+    for (int i = 0; i < m; ++i) {
+      double next      = y[i] - (sigma * Ax[i]);
+      const double low = next + sigma * lcs[i];
+      const double up  = next + sigma * ucs[i];
+      next             = std::max(low, std::min(up, 0.0));
+      yn[i]            = next;
+      dy[i]            = next - y[i];
+    }
+  }
+  // adaptive_step_size_strategy.cu:232-345
+  void interaction_and_movement()
+  {
+    spmv(ATs, yn.data(), AtYn.data());
+    interaction = reduce_sum(n, [&](int j) { return (AtYn[j] - AtY[j]) * dx[j]; });
+    norm_dx2    = reduce_sum(n, [&](int j) { return dx[j] * dx[j]; });
+    norm_dy2    = reduce_sum(m, [&](int i) { return dy[i] * dy[i]; });
+  }
+  // adaptive_step_size_strategy.cu:92-188
+  void step_sizes_from_movement_and_interaction()
+  {
+    const double movement =
+      hp.primal_distance_smoothing * primal_weight * norm_dx2 + (hp.dual_distance_smoothing / primal_weight) * norm_dy2;
+    if (movement <= 0.0 || movement >= 1.0e100) {
+      valid_step_size = -1;
+      return;
+    }
+    const double inter = std::fabs(interaction);
+    double eta         = step_size;
+    k_pdhg_dev += 1;
+    const double kcoef = (double)k_pdhg_dev;
+    const double limit = inter > 0.0 ? movement / inter : kInf;
+    if (eta <= limit) valid_step_size = 1;
+    const double cand1 = (1.0 - std::pow(kcoef + 1.0, -hp.reduction_exponent)) * limit;
+    const double cand2 = (1.0 + std::pow(kcoef + 1.0, -hp.growth_exponent)) * eta;
+    eta                = std::min(cand1, cand2);
+    tau                = eta / primal_weight;
+    sigma              = eta * primal_weight;
+    step_size          = eta;
+  }
+  // pdlp.cu:1188-1222
+  void take_step()
+  {
+    valid_step_size = 0;
+    while (valid_step_size == 0) {
+      // pdhg.cu:183-202: A^T y only on the very first step or right after a restart to the average
+      if (k_pdhg_host == 0 || (its_since_restart == 0 && last_restart_was_average)) spmv(ATs, y.data(), AtY.data());
+      primal_projection();
+      dual_projection();
+      k_pdhg_host += 1;  // pdhg.cu:234
+      interaction_and_movement();
+      step_sizes_from_movement_and_interaction();
+    }
+    // weighted_average_solution.cu:73-110, weight = the step size AFTER its update (pdlp.cu:1216-1219)
+    const double w = step_size;
+#pragma omp parallel for schedule(static) if (n > 20000)
+    for (int j = 0; j < n; ++j) sum_x[j] = sum_x[j] + w * xn[j];
+#pragma omp parallel for schedule(static) if (m > 20000)
+    for (int i = 0; i < m; ++i) sum_y[i] = sum_y[i] + w * yn[i];
+    sum_w += w;
+    its_since_restart += 1;
+    x.swap(xn);  // pdhg.cu:238-250
+    y.swap(yn);
+    AtY.swap(AtYn);
+  }
+
+  // --------------------------------------------------- termination evaluation
+  // convergence_information.cu:150-422 on the UNSCALED problem; px / py are unscaled iterates.
+  void compute_convergence_information(const std::vector<double>& px, const std::vector<double>& py, convergence_t& cv)
+  {
+    // primal residual (:222-250), objective (:262-286)
+    spmv(A, px.data(), tmp_m.data());
+    cv.l2_primal_residual = std::sqrt(reduce_sum(m, [&](int i) {
+      const double v = violation(tmp_m[i], lc[i], uc[i]);
+      return v * v;
+    }));
+    cv.primal_objective = reduce_sum(n, [&](int j) { return px[j] * c[j]; });
+    if (obj_scale != 1.0 || obj_offset != 0.0) cv.primal_objective = obj_scale * cv.primal_objective + obj_offset;
+    cv.l2_primal_variable = std::sqrt(reduce_sum(n, [&](int j) { return px[j] * px[j]; }));
+    // dual residual (:288-322): g = c - A^T y ; reduced cost (:371-398)
+    spmv(AT, py.data(), tmp_n.data());
+    for (int j = 0; j < n; ++j) {
+      const double g = c[j] - tmp_n[j];
+      tmp_n[j]       = g;
+      // utils.cuh:196-202 (the g>0 && g<0 test there can never hold)
+      const double bound_value = g > 0.0 ? l[j] : u[j];
+      double rc;
+      if (hp.handle_some_primal_gradients_on_finite_bounds_as_residuals) {  // utils.cuh:222-229
+        if (g == 0.0) rc = g;
+        else if (std::fabs(px[j] - bound_value) <= std::fabs(px[j])) rc = g;
+        else rc = 0.0;
+      } else {  // utils.cuh:232-239
+        if (g == 0.0) rc = g;
+        else if (std::isfinite(bound_value)) rc = g;
+        else rc = 0.0;
+      }
+      cv.reduced_cost[j] = rc;
+    }
+    cv.l2_dual_residual = std::sqrt(reduce_sum(n, [&](int j) {
+      const double r = tmp_n[j] - cv.reduced_cost[j];
+      return r * r;
+    }));
+    // dual objective (:324-369, :400-422)
+    double dobj = reduce_sum(m, [&](int i) { return bound_value_reduced_cost_product(py[i], lc[i], uc[i]); });
+    dobj += reduce_sum(n, [&](int j) { return bound_value_reduced_cost_product(cv.reduced_cost[j], l[j], u[j]); });
+    if (obj_scale != 1.0 || obj_offset != 0.0) dobj = obj_scale * dobj + obj_offset;
+    cv.dual_objective    = dobj;
+    cv.l2_dual_variable  = std::sqrt(reduce_sum(m, [&](int i) { return py[i] * py[i]; }));
+    cv.gap               = std::fabs(cv.primal_objective - cv.dual_objective);  // :137-148
+    cv.abs_objective     = std::fabs(cv.primal_objective) + std::fabs(cv.dual_objective);
+    // termination_strategy.cu:117-250 (per_constraint_residual = false, no infeasibility detection)
+    cv.status              = 6;  // "NumericalError" == keep going (:186)
+    const bool optimal_gap = cv.gap <= st.abs_gap_tol + st.rel_gap_tol * cv.abs_objective;
+    const bool primal_feas = cv.l2_primal_residual <= st.abs_primal_tol + st.rel_primal_tol * l2_norm_b;
+    const bool dual_feas   = cv.l2_dual_residual <= st.abs_dual_tol + st.rel_dual_tol * l2_norm_c;
+    if (dual_feas && primal_feas && optimal_gap) cv.status = 1;
+    else if (primal_feas) cv.status = 7;
+  }
+
+  // pdlp_restart_strategy.cu:367-405
+  double kkt_score(const convergence_t& cv) const
+  {
+    const double w2 = primal_weight * primal_weight;
+    return std::sqrt(w2 * cv.l2_primal_residual * cv.l2_primal_residual +
+                     cv.l2_dual_residual * cv.l2_dual_residual / w2 + cv.gap * cv.gap);
+  }
+
+  void fill_solution(const std::vector<double>& px, const std::vector<double>& py, const convergence_t& cv, int status,
+                     bool is_avg)
+  {
+    // termination_strategy.cu:270-357
+    sol_x  = px;
+    sol_y  = py;
+    sol_rc = cv.reduced_cost;
+    result.termination_status              = status;
+    result.number_of_steps_taken           = k_internal;
+    result.total_number_of_attempted_steps = k_pdhg_host;
+    result.primal_objective                = cv.primal_objective;
+    result.dual_objective                  = cv.dual_objective;
+    result.gap                             = cv.gap;
+    result.relative_gap                    = cv.gap / (1.0 + std::fabs(cv.primal_objective) + std::fabs(cv.dual_objective));
+    result.l2_primal_residual              = cv.l2_primal_residual;
+    result.l2_dual_residual                = cv.l2_dual_residual;
+    result.l2_relative_primal_residual     = cv.l2_primal_residual / (1.0 + l2_norm_b);
+    result.l2_relative_dual_residual       = cv.l2_dual_residual / (1.0 + l2_norm_c);
+    result.step_size                       = step_size;
+    result.primal_weight                   = primal_weight;
+    result.n_restarts                      = n_restarts;
+    result.n_major                         = n_major;
+    result.solution_is_average             = is_avg ? 1 : 0;
+  }
+
+  // pdlp.cu:265-331 (time limit is evaluated by the caller's clock)
+  bool check_limits(double elapsed)
+  {
+    if (elapsed >= st.time_limit) {
+      fill_solution(x, y, conv_cur, 5, false);
+      return true;
+    }
+    if (k_internal >= st.iteration_limit) {
+      fill_solution(x, y, conv_cur, 4, false);
+      return true;
+    }
+    return false;
+  }
+
+  // pdlp.cu:538-802 (first_primal_feasible / save_best_primal_so_far / infeasibility detection off)
+  bool check_termination(double elapsed)
+  {
+    compute_convergence_information(x, y, conv_cur);
+    compute_convergence_information(x_avg, y_avg, conv_avg);
+    if (k_total <= 1) return check_limits(elapsed);  // :580-583
+    const bool cur_opt = conv_cur.status == 1, avg_opt = conv_avg.status == 1;
+    if (cur_opt && avg_opt) {  // :636-682
+      if (kkt_score(conv_cur) < kkt_score(conv_avg)) fill_solution(x, y, conv_cur, 1, false);
+      else fill_solution(x_avg, y_avg, conv_avg, 1, true);
+      return true;
+    }
+    if (avg_opt) { fill_solution(x_avg, y_avg, conv_avg, 1, true); return true; }   // :685-700
+    if (cur_opt) { fill_solution(x, y, conv_cur, 1, false); return true; }          // :701-716
+    if (valid_step_size == -1) {  // :780-789: error solution (empty vectors)
+      result                    = stats_t{};
+      result.termination_status = 6;
+      result.number_of_steps_taken           = k_internal;
+      result.total_number_of_attempted_steps = k_pdhg_host;
+      sol_x.assign(n, 0.0); sol_y.assign(m, 0.0); sol_rc.assign(n, 0.0);
+      return true;
+    }
+    return check_limits(elapsed);
+  }
+
+  bool should_do_artificial_restart(int total_iterations) const  // pdlp_restart_strategy.cu:940-961
+  {
+    return its_since_restart >= hp.artificial_restart_threshold * total_iterations;
+  }
+  bool kkt_decay(double cand) const  // :408-429
+  {
+    if (cand < hp.sufficient_reduction_for_restart * last_restart_kkt) return true;
+    if (cand < hp.necessary_reduction_for_restart * last_restart_kkt && cand > last_candidate_kkt) return true;
+    return false;
+  }
+
+  // pdlp_restart_strategy.cu:468-641; x/y and x_avg/y_avg are in the space pdlp.cu:1144-1149 left them in
+  // (scaled when rescale_for_restart, otherwise still unscaled — the reference's behaviour).
+  void run_kkt_restart(trace_row_t& tr)
+  {
+    const double cur = kkt_score(conv_cur);
+    tr.kkt_current   = cur;
+    if (its_since_restart == 0) {  // :505-513
+      last_candidate_kkt = cur;
+      last_restart_kkt   = cur;
+      return;
+    }
+    const double avg = kkt_score(conv_avg);
+    tr.kkt_average   = avg;
+    bool to_avg;
+    double cand;
+    if (cur < avg) { to_avg = false; cand = cur; } else { to_avg = true; cand = avg; }
+    if (should_do_artificial_restart(k_total) || kkt_decay(cand)) {
+      const bool use_avg               = to_avg && !hp.never_restart_to_average;
+      const std::vector<double>& candx = use_avg ? x_avg : x;
+      const std::vector<double>& candy = use_avg ? y_avg : y;
+      // :753-801, 1681-1714: plain L2 distance to the last restart point
+      const double dprim = reduce_sum(n, [&](int j) { const double d = x_lr[j] - candx[j]; return d * d; });
+      const double ddual = reduce_sum(m, [&](int i) { const double d = y_lr[i] - candy[i]; return d * d; });
+      if (use_avg) {  // :587-599
+        x = x_avg;
+        y = y_avg;
+        last_restart_was_average = true;
+      } else {
+        last_restart_was_average = false;
+      }
+      auto new_primal_weight = [&]() {  // :685-732
+        const double pd = std::sqrt(dprim), dd = std::sqrt(ddual);
+        const double guard = 1.0e-10;
+        if (pd < guard || pd >= 1.0 / guard || dd < guard || dd >= 1.0 / guard) return;
+        const double est = dd / pd;
+        const double lw  = hp.primal_weight_update_smoothing * std::log(est) +
+                          (1.0 - hp.primal_weight_update_smoothing) * std::log(primal_weight);
+        primal_weight = std::exp(lw);
+        tau           = step_size / primal_weight;
+        sigma         = step_size * primal_weight;
+      };
+      // :601-611: the two orders differ only in which primal weight feeds `distance_traveled`, a quantity
+      // the KKT scheme never reads, so both collapse to: store the restart point, update the weight.
+      x_lr = x;  // x already holds the candidate (either untouched current, or the average copied above)
+      y_lr = y;
+      new_primal_weight();
+      std::fill(sum_x.begin(), sum_x.end(), 0.0);  // weighted_average_solution.cu:51-60
+      std::fill(sum_y.begin(), sum_y.end(), 0.0);
+      sum_w             = 0.0;
+      its_since_restart = 0;
+      last_restart_kkt  = cand;
+      n_restarts += 1;
+      tr.restarted  = 1;
+      tr.to_average = use_avg ? 1 : 0;
+    }
+    last_candidate_kkt = cand;
+  }
+
+  // -------------------------------------------------------- outer loop
+  // pdlp.cu:1081-1185.  Runs until termination or until `max_accepted_steps` more PDLP iterations
+  // have been taken (used by the step-by-step parity tests).  Returns true when a solution was filled.
+  bool run(int max_accepted_steps)
+  {
+    if (!initialised) initialise();
+    const auto t0 = std::chrono::steady_clock::now();
+    int budget    = max_accepted_steps;
+    while (true) {
+      const bool is_major = ((k_total % hp.major_iteration == 0) && (k_total > 0)) || (k_total <= hp.min_iteration_restart);
+      const bool error    = (valid_step_size == -1);
+      bool artificial     = false;
+      if (hp.artificial_restart_in_main_loop) artificial = should_do_artificial_restart(k_total);
+      if (is_major || artificial || error) {
+        n_major += 1;
+        trace_row_t tr{};
+        tr.k = k_total;
+        if (k_internal <= 1) {  // :1110-1118
+          x_avg = x;
+          y_avg = y;
+        } else {  // weighted_average_solution.cu:114-142
+          if (its_since_restart == 0) {
+            std::fill(x_avg.begin(), x_avg.end(), 0.0);
+            std::fill(y_avg.begin(), y_avg.end(), 0.0);
+          } else {
+            for (int j = 0; j < n; ++j) x_avg[j] = sum_x[j] / sum_w;
+            for (int i = 0; i < m; ++i) y_avg[i] = sum_y[i] / sum_w;
+          }
+        }
+        unscale_solutions(x_avg, y_avg);  // :1131-1136
+        unscale_solutions(x, y);
+        const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const bool done      = check_termination(elapsed);
+        tr.primal_objective = conv_cur.primal_objective; tr.dual_objective = conv_cur.dual_objective;
+        tr.gap = conv_cur.gap; tr.l2_primal_residual = conv_cur.l2_primal_residual;
+        tr.l2_dual_residual = conv_cur.l2_dual_residual; tr.step_size = step_size; tr.primal_weight = primal_weight;
+        if (done) {
+          trace.push_back(tr);
+          result.solve_seconds = elapsed;
+          return true;
+        }
+        if (hp.rescale_for_restart) {  // :1144-1149
+          scale_solutions(x_avg, y_avg);
+          scale_solutions(x, y);
+        }
+        if (hp.restart_strategy == 1) run_kkt_restart(tr);
+        if (!hp.rescale_for_restart) scale_solutions(x, y);  // :1168-1175
+        trace.push_back(tr);
+      }
+      if (budget == 0) return false;
+      take_step();
+      ++k_total;
+      ++k_internal;
+      if (budget > 0) --budget;
+    }
+  }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI (ctypes)
+extern "C" {
+
+void* pdlp_oracle_create(int m, int n, const int* off, const int* idx, const double* val, const double* c,
+                         const double* l, const double* u, const double* lc, const double* uc, int maximize,
+                         double objective_offset, const hyper_t* hp, const settings_t* st)
+{
+  return new oracle_t(m, n, off, idx, val, c, l, u, lc, uc, maximize, objective_offset, *hp, *st);
+}
+void pdlp_oracle_destroy(void* h) { delete static_cast<oracle_t*>(h); }
+void pdlp_oracle_initialise(void* h) { static_cast<oracle_t*>(h)->initialise(); }
+// returns 1 if terminated (solution filled), 0 if the step budget ran out first. max_steps < 0: run to the end.
+int pdlp_oracle_run(void* h, int max_steps) { return static_cast<oracle_t*>(h)->run(max_steps) ? 1 : 0; }
+void pdlp_oracle_stats(void* h, stats_t* out) { *out = static_cast<oracle_t*>(h)->result; }
+
+// One PDHG attempt from caller-supplied scaled state (kernel-level parity tests): computes
+// x', xbar, y', AtY', the three reductions; no accept/reject, no state mutation besides the buffers.
+void pdlp_oracle_single_attempt(void* h, const double* x, const double* y, const double* aty, double tau, double sigma,
+                                double* xn, double* xbar, double* yn, double* atyn, double* red3)
+{
+  auto* o = static_cast<oracle_t*>(h);
+  oracle_t& s = *o;
+  std::vector<double> sx = s.x, sy = s.y, saty = s.AtY;
+  const double stau = s.tau, ssig = s.sigma;
+  s.x.assign(x, x + s.n); s.y.assign(y, y + s.m); s.AtY.assign(aty, aty + s.n);
+  s.tau = tau; s.sigma = sigma;
+  s.primal_projection();
+  s.dual_projection();
+  s.interaction_and_movement();
+  std::memcpy(xn, s.xn.data(), sizeof(double) * s.n);
+  std::memcpy(xbar, s.xbar.data(), sizeof(double) * s.n);
+  std::memcpy(yn, s.yn.data(), sizeof(double) * s.m);
+  std::memcpy(atyn, s.AtYn.data(), sizeof(double) * s.n);
+  red3[0] = s.interaction; red3[1] = s.norm_dx2; red3[2] = s.norm_dy2;
+  s.x = sx; s.y = sy; s.AtY = saty; s.tau = stau; s.sigma = ssig;
+}
+
+// Evaluate the termination quantities for an UNSCALED iterate: out[0..7] = l2_primal_residual, l2_dual_residual,
+// primal_objective, dual_objective, gap, abs_objective, status, kkt(primal_weight as currently held)
+void pdlp_oracle_convergence(void* h, const double* px, const double* py, double* out8, double* reduced_cost)
+{
+  auto* o = static_cast<oracle_t*>(h);
+  if (o->tmp_m.size() != (size_t)o->m) { o->tmp_m.assign(o->m, 0.0); o->tmp_n.assign(o->n, 0.0); }
+  convergence_t cv;
+  cv.reduced_cost.assign(o->n, 0.0);
+  std::vector<double> vx(px, px + o->n), vy(py, py + o->m);
+  o->compute_convergence_information(vx, vy, cv);
+  out8[0] = cv.l2_primal_residual; out8[1] = cv.l2_dual_residual; out8[2] = cv.primal_objective;
+  out8[3] = cv.dual_objective; out8[4] = cv.gap; out8[5] = cv.abs_objective; out8[6] = cv.status;
+  out8[7] = o->primal_weight > 0 ? o->kkt_score(cv) : 0.0;
+  if (reduced_cost) std::memcpy(reduced_cost, cv.reduced_cost.data(), sizeof(double) * o->n);
+}
+
+// Named vectors / scalars for white-box comparisons.
+int pdlp_oracle_get_vector(void* h, const char* name, double* out)
+{
+  auto* o = static_cast<oracle_t*>(h);
+  const std::string s(name);
+  const std::vector<double>* v = nullptr;
+  if (s == "x") v = &o->x; else if (s == "y") v = &o->y; else if (s == "aty") v = &o->AtY;
+  else if (s == "sum_x") v = &o->sum_x; else if (s == "sum_y") v = &o->sum_y;
+  else if (s == "x_avg") v = &o->x_avg; else if (s == "y_avg") v = &o->y_avg;
+  else if (s == "row_scaling") v = &o->Dr; else if (s == "col_scaling") v = &o->Dc;
+  else if (s == "scaled_values") v = &o->As.val; else if (s == "scaled_values_t") v = &o->ATs.val;
+  else if (s == "scaled_c") v = &o->cs; else if (s == "scaled_l") v = &o->ls; else if (s == "scaled_u") v = &o->us;
+  else if (s == "scaled_lc") v = &o->lcs; else if (s == "scaled_uc") v = &o->ucs;
+  else if (s == "solution_x") v = &o->sol_x; else if (s == "solution_y") v = &o->sol_y;
+  else if (s == "solution_rc") v = &o->sol_rc;
+  else if (s == "x_last_restart") v = &o->x_lr; else if (s == "y_last_restart") v = &o->y_lr;
+  if (!v) return -1;
+  if (out) std::memcpy(out, v->data(), sizeof(double) * v->size());
+  return (int)v->size();
+}
+double pdlp_oracle_get_scalar(void* h, const char* name)
+{
+  auto* o = static_cast<oracle_t*>(h);
+  const std::string s(name);
+  if (s == "step_size") return o->step_size;
+  if (s == "primal_weight") return o->primal_weight;
+  if (s == "tau") return o->tau;
+  if (s == "sigma") return o->sigma;
+  if (s == "sum_w") return o->sum_w;
+  if (s == "k_total") return o->k_total;
+  if (s == "k_pdhg") return o->k_pdhg_host;
+  if (s == "its_since_restart") return o->its_since_restart;
+  if (s == "interaction") return o->interaction;
+  if (s == "norm_dx2") return o->norm_dx2;
+  if (s == "norm_dy2") return o->norm_dy2;
+  if (s == "l2_norm_b") return o->l2_norm_b;
+  if (s == "l2_norm_c") return o->l2_norm_c;
+  if (s == "last_restart_kkt") return o->last_restart_kkt;
+  if (s == "last_candidate_kkt") return o->last_candidate_kkt;
+  if (s == "n_restarts") return o->n_restarts;
+  return std::numeric_limits<double>::quiet_NaN();
+}
+// Major-iteration trace: 12 doubles per row (k, restarted, to_average, p, d, gap, rp, rd, step, weight, kkt_cur, kkt_avg)
+int pdlp_oracle_trace(void* h, double* out, int max_rows)
+{
+  auto* o   = static_cast<oracle_t*>(h);
+  const int r = (int)o->trace.size();
+  if (out) {
+    for (int i = 0; i < std::min(r, max_rows); ++i) {
+      const auto& t = o->trace[i];
+      double* p     = out + 12 * i;
+      p[0] = t.k; p[1] = t.restarted; p[2] = t.to_average; p[3] = t.primal_objective; p[4] = t.dual_objective;
+      p[5] = t.gap; p[6] = t.l2_primal_residual; p[7] = t.l2_dual_residual; p[8] = t.step_size;
+      p[9] = t.primal_weight; p[10] = t.kkt_current; p[11] = t.kkt_average;
+    }
+  }
+  return r;
+}
+
+}  // extern "C"
