@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""bench.py — PDLP iterations/sec on BASELINE.json's configs[1] (synthetic sparse LP, 1M x 1M, 8 nnz/row, fp64).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference PDLP on host cores
+
+A "step" = one solve of ITERS_PER_STEP PDLP iterations on the resident LP (tolerances 0 => never stops early).
+  value  = accepted PDLP iterations / device time of the solver loop (CUDA events, inputs resident in HBM)
+  e2e    = the same through cuOptCreateRangedProblem + cuOptSolve + cuOptGet*Solution with HOST buffers:
+           H2D upload, transpose, diagonal scaling and D2H of the solution are inside the timed region
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pdlp_iterations_per_sec"
+UNIT = "iterations/s"
+ITERS_PER_STEP = 2000
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args):
+    from cuopt_b200 import lpgen
+    return lpgen.sparse_lp(args.rows, args.cols, args.nnz_per_row, seed=1234)
+
+
+def config_dict(args, lp, n_gpus):
+    return {"workload": f"configs[1]: synthetic random sparse LP {lp.m}x{lp.n}, {args.nnz_per_row} nnz/row, fp64, "
+                        f"planted optimum (cuopt_b200.lpgen.sparse_lp seed 1234)",
+            "rows": lp.m, "cols": lp.n, "nnz": lp.nnz, "iterations_per_step": args.iters,
+            "pdlp_solver_mode": "Stable2", "parallelism": f"replicas x{n_gpus}" if n_gpus > 1 else "1 GPU",
+            "l2_policy": "per-iteration working set (A, A^T, 14 vectors = %.0f MB) exceeds the 126 MB L2"
+                         % (lp.algorithmic_bytes_per_iteration() / 1e6)}
+
+
+def run_reference(args):
+    """CPU arm: the reference's PDLP as restated by the oracle port, all host threads, bounded sample."""
+    from oracle import pdlp_oracle as po
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lp = workload(args)
+    cores = os.cpu_count() or 1
+    o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=0.0)
+    o.initialise()
+    sample = args.cpu_iters
+    for _ in range(args.warmup):
+        o.run(5)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        o.run(sample)
+        done += sample
+    dt = time.perf_counter() - t0
+    v = done / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args, lp, 1),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} PDLP iterations per step of the same LP (oracle/pdlp_oracle.cpp, OpenMP)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--cols", type=int, default=1_000_000)
+    ap.add_argument("--nnz-per-row", type=int, default=8)
+    ap.add_argument("--iters", type=int, default=ITERS_PER_STEP)
+    ap.add_argument("--cpu-iters", type=int, default=60, help="oracle iterations per step (CPU arm / cpu_baseline)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-reps", type=int, default=200)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from cuopt_b200 import capi
+
+    lp = workload(args)
+    settings = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False, iteration_limit=args.iters)
+    settings.set("optimality_tolerance", 0.0)  # never stop early: every step runs exactly `iters` iterations
+
+    def one_step():
+        # e2e path: HOST numpy buffers -> C ABI -> HOST result buffers
+        p = capi.Problem.create_ranged(lp.offsets, lp.indices, lp.values, lp.con_lb, lp.con_ub, lp.c, lp.var_lb,
+                                       lp.var_ub)
+        sol = capi.solve(p, settings)
+        if sol.return_code != 0:
+            raise RuntimeError(sol.error_string)
+        x = sol.primal(); y = sol.dual()
+        st = sol.stats()
+        return st, float(x[0] + y[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    its = 0; dev_s = 0.0; launches = 0; setup_s = 0.0
+    for _ in range(args.steps):
+        st, _ = one_step()
+        its += st.number_of_steps_taken
+        dev_s += st.pdhg_loop_seconds + st.termination_seconds
+        setup_s += st.setup_seconds
+        launches += st.kernel_launches
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks (device time and wall), sum of iterations
+    if world > 1:
+        t = torch.tensor([dev_s, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, wall = float(t[0]), float(t[1])
+        c = torch.tensor([its, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        its, launches = int(c[0]), int(c[1])
+
+    # roofline of the dominant kernel, measured in situ with CUDA events on the solver's stream
+    roof = None
+    cpu = None
+    extra = {}
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        p = capi.Problem.create_ranged(lp.offsets, lp.indices, lp.values, lp.con_lb, lp.con_ub, lp.c, lp.var_lb, lp.var_ub)
+        prof = capi.Solver(p, settings).profile_kernels(120, args.profile_reps)
+        ks = {"k_primal_step": (prof.ms_primal_step, prof.bytes_primal_step),
+              "k_dual_step": (prof.ms_dual_step, prof.bytes_dual_step),
+              "k_transpose_step": (prof.ms_transpose_step, prof.bytes_transpose_step)}
+        dom = max(ks, key=lambda k: ks[k][0])
+        ms, by = ks[dom]
+        achieved = by / (ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                "algorithmic_bytes_per_launch": by, "ms_per_launch": ms}
+        b_iter = lp.algorithmic_bytes_per_iteration()
+        extra = {"kernels": {k: {"ms": v[0], "algorithmic_GBps": v[1] / (v[0] * 1e-3) / 1e9} for k, v in ks.items()},
+                 "iteration": {"ms_in_batch": prof.ms_iteration, "algorithmic_bytes": b_iter,
+                               "algorithmic_GBps": b_iter / (prof.ms_iteration * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": b_iter / (prof.ms_iteration * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                 "grids": {"primal": prof.grid_primal, "dual": prof.grid_dual, "transpose": prof.grid_transpose},
+                 "setup_seconds_per_step": setup_s / args.steps}
+        if not args.no_cpu_baseline and world == 1 or (not args.no_cpu_baseline and rank == 0):
+            from oracle import pdlp_oracle as po
+            o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=0.0)
+            o.initialise(); o.run(5)
+            tc = time.perf_counter(); o.run(args.cpu_iters * 3); tc = time.perf_counter() - tc
+            cpu = {"value": args.cpu_iters * 3 / tc, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"{args.cpu_iters * 3} PDLP iterations of the same LP by oracle/pdlp_oracle.cpp (OpenMP)"}
+
+    if rank == 0:
+        h2d = 12 * lp.nnz * 2 + 4 * (lp.m + lp.n + 2) + 8 * (3 * lp.n + 2 * lp.m)
+        d2h = 8 * (2 * lp.n + lp.m)
+        out = {"metric": METRIC, "value": its / dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": config_dict(args, lp, world), "clocks": clocks,
+               "e2e": {"value": its / wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "detail": extra}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,623 @@
+// extern "C" boundary: the 41 reference symbols of cuopt_c.h plus the cuOptB200* extension.
+// Semantics follow cpp/src/linear_programming/cuopt_c.cpp of the reference (line tags below).
+#include <cuopt_b200/cuopt_b200_ext.h>
+
+#include "lp_problem.hpp"
+#include "pdlp_solver.hpp"
+#include "solver_settings.hpp"
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+
+using namespace cuopt_b200;
+
+namespace {
+
+struct solution_handle_t {
+  lp_solution_t sol;
+  bool is_mip = false;
+};
+
+struct solver_handle_t {
+  std::unique_ptr<pdlp_solver_t> solver;
+  bool finished = false;
+};
+
+template <typename T>
+void copy_out(T* dst, const std::vector<T>& src)
+{
+  if (!src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(T));
+}
+
+cuopt_int_t fill_problem_common(lp_problem_t& p,
+                                cuopt_int_t m,
+                                cuopt_int_t n,
+                                cuopt_int_t sense,
+                                cuopt_float_t offset,
+                                const cuopt_float_t* c,
+                                const cuopt_int_t* off,
+                                const cuopt_int_t* idx,
+                                const cuopt_float_t* val,
+                                const cuopt_float_t* lb,
+                                const cuopt_float_t* ub,
+                                const char* types)
+{
+  if (m < 0 || n < 0) return CUOPT_INVALID_ARGUMENT;
+  p.n_constraints    = m;
+  p.n_variables      = n;
+  p.maximize         = (sense == CUOPT_MAXIMIZE);
+  p.objective_offset = offset;
+  p.objective_coefficients.assign(c, c + n);
+  const cuopt_int_t nnz = off[m];
+  if (nnz < 0) return CUOPT_INVALID_ARGUMENT;
+  p.A_offsets.assign(off, off + m + 1);
+  p.A_indices.assign(idx, idx + nnz);
+  p.A_values.assign(val, val + nnz);
+  p.variable_lower_bounds.assign(lb, lb + n);
+  p.variable_upper_bounds.assign(ub, ub + n);
+  p.variable_types.resize(n);
+  for (int j = 0; j < n; ++j) p.variable_types[j] = types[j] == CUOPT_CONTINUOUS ? 'C' : 'I';  // cuopt_c.cpp:127-131
+  return CUOPT_SUCCESS;
+}
+
+// reference log line formats: pdlp.cu:1078-1080, termination_strategy.cu:380-390, solve.cu:376-380
+void log_solution(const pdlp_settings_t& st, const lp_problem_t& p, const lp_solution_t& s)
+{
+  auto emit = [&](FILE* f) {
+    std::fprintf(f, "Solving a problem with %d constraints %d variables (%d integers) and %d nonzeros\n", p.n_constraints,
+                 p.n_variables, 0, p.nnz());
+    std::fprintf(f, "   Iter    Primal Obj.      Dual Obj.    Gap        Primal Res.  Dual Res.   Time\n");
+    std::fprintf(f, "%7d %+.8e %+.8e  %8.2e   %8.2e     %8.2e   %.3fs\n", s.stats.number_of_steps_taken,
+                 s.stats.primal_objective, s.stats.dual_objective, s.stats.gap, s.stats.l2_primal_residual,
+                 s.stats.l2_dual_residual, s.stats.solve_time);
+    std::fprintf(f, "PDLP finished\n");
+    std::fprintf(f, "Status: %s   Objective: %.8e  Iterations: %d  Time: %.3fs\n",
+                 termination_status_string(s.termination_status), s.stats.primal_objective,
+                 s.stats.number_of_steps_taken, s.stats.solve_time);
+  };
+  if (st.log_to_console) emit(stdout);
+  if (!st.log_file.empty()) {
+    if (FILE* f = std::fopen(st.log_file.c_str(), "w")) {
+      emit(f);
+      std::fclose(f);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int8_t cuOptGetFloatSize() { return sizeof(cuopt_float_t); }
+int8_t cuOptGetIntSize() { return sizeof(cuopt_int_t); }
+
+cuopt_int_t cuOptReadProblem(const char* filename, cuOptOptimizationProblem* problem_ptr)  // cuopt_c.cpp:62-86
+{
+  if (filename == nullptr || problem_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  *problem_ptr = nullptr;
+  try {
+    auto* p      = new lp_problem_t(read_mps(filename, false));
+    *problem_ptr = p;
+    return CUOPT_SUCCESS;
+  } catch (const lp_error& e) {
+    return e.type == error_type_t::MpsFileError ? CUOPT_MPS_FILE_ERROR : CUOPT_MPS_PARSE_ERROR;
+  } catch (const std::exception&) {
+    return CUOPT_MPS_PARSE_ERROR;
+  }
+}
+
+cuopt_int_t cuOptCreateProblem(cuopt_int_t num_constraints,
+                               cuopt_int_t num_variables,
+                               cuopt_int_t objective_sense,
+                               cuopt_float_t objective_offset,
+                               const cuopt_float_t* objective_coefficients,
+                               const cuopt_int_t* constraint_matrix_row_offsets,
+                               const cuopt_int_t* constraint_matrix_column_indices,
+                               const cuopt_float_t* constraint_matrix_coefficent_values,
+                               const char* constraint_sense,
+                               const cuopt_float_t* rhs,
+                               const cuopt_float_t* lower_bounds,
+                               const cuopt_float_t* upper_bounds,
+                               const char* variable_types,
+                               cuOptOptimizationProblem* problem_ptr)  // cuopt_c.cpp:88-141
+{
+  if (problem_ptr == nullptr || objective_coefficients == nullptr || constraint_matrix_row_offsets == nullptr ||
+      constraint_matrix_column_indices == nullptr || constraint_matrix_coefficent_values == nullptr ||
+      constraint_sense == nullptr || rhs == nullptr || lower_bounds == nullptr || upper_bounds == nullptr ||
+      variable_types == nullptr)
+    return CUOPT_INVALID_ARGUMENT;
+  try {
+    auto p = std::make_unique<lp_problem_t>();
+    if (auto rc = fill_problem_common(*p, num_constraints, num_variables, objective_sense, objective_offset,
+                                      objective_coefficients, constraint_matrix_row_offsets,
+                                      constraint_matrix_column_indices, constraint_matrix_coefficent_values, lower_bounds,
+                                      upper_bounds, variable_types))
+      return rc;
+    p->row_types.assign(constraint_sense, constraint_sense + num_constraints);
+    p->constraint_bounds.assign(rhs, rhs + num_constraints);
+    *problem_ptr = p.release();
+  } catch (const std::exception&) {
+    return CUOPT_INVALID_ARGUMENT;
+  }
+  return CUOPT_SUCCESS;
+}
+
+cuopt_int_t cuOptCreateRangedProblem(cuopt_int_t num_constraints,
+                                     cuopt_int_t num_variables,
+                                     cuopt_int_t objective_sense,
+                                     cuopt_float_t objective_offset,
+                                     const cuopt_float_t* objective_coefficients,
+                                     const cuopt_int_t* constraint_matrix_row_offsets,
+                                     const cuopt_int_t* constraint_matrix_column_indices,
+                                     const cuopt_float_t* constraint_matrix_coefficients,
+                                     const cuopt_float_t* constraint_lower_bounds,
+                                     const cuopt_float_t* constraint_upper_bounds,
+                                     const cuopt_float_t* variable_lower_bounds,
+                                     const cuopt_float_t* variable_upper_bounds,
+                                     const char* variable_types,
+                                     cuOptOptimizationProblem* problem_ptr)  // cuopt_c.cpp:143-198
+{
+  if (problem_ptr == nullptr || objective_coefficients == nullptr || constraint_matrix_row_offsets == nullptr ||
+      constraint_matrix_column_indices == nullptr || constraint_matrix_coefficients == nullptr ||
+      constraint_lower_bounds == nullptr || constraint_upper_bounds == nullptr || variable_lower_bounds == nullptr ||
+      variable_upper_bounds == nullptr || variable_types == nullptr)
+    return CUOPT_INVALID_ARGUMENT;
+  try {
+    auto p = std::make_unique<lp_problem_t>();
+    if (auto rc = fill_problem_common(*p, num_constraints, num_variables, objective_sense, objective_offset,
+                                      objective_coefficients, constraint_matrix_row_offsets,
+                                      constraint_matrix_column_indices, constraint_matrix_coefficients,
+                                      variable_lower_bounds, variable_upper_bounds, variable_types))
+      return rc;
+    p->constraint_lower_bounds.assign(constraint_lower_bounds, constraint_lower_bounds + num_constraints);
+    p->constraint_upper_bounds.assign(constraint_upper_bounds, constraint_upper_bounds + num_constraints);
+    *problem_ptr = p.release();
+  } catch (const std::exception&) {
+    return CUOPT_INVALID_ARGUMENT;
+  }
+  return CUOPT_SUCCESS;
+}
+
+void cuOptDestroyProblem(cuOptOptimizationProblem* problem_ptr)  // cuopt_c.cpp:200-206
+{
+  if (problem_ptr == nullptr || *problem_ptr == nullptr) return;
+  delete static_cast<lp_problem_t*>(*problem_ptr);
+  *problem_ptr = nullptr;
+}
+
+#define PROBLEM_OR_FAIL(out)                                             \
+  if (problem == nullptr || (out) == nullptr) return CUOPT_INVALID_ARGUMENT; \
+  const lp_problem_t& p = *static_cast<const lp_problem_t*>(problem)
+
+cuopt_int_t cuOptGetNumConstraints(cuOptOptimizationProblem problem, cuopt_int_t* num_constraints_ptr)
+{
+  PROBLEM_OR_FAIL(num_constraints_ptr);
+  *num_constraints_ptr = p.n_constraints;
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetNumVariables(cuOptOptimizationProblem problem, cuopt_int_t* num_variables_ptr)
+{
+  PROBLEM_OR_FAIL(num_variables_ptr);
+  *num_variables_ptr = p.n_variables;
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetObjectiveSense(cuOptOptimizationProblem problem, cuopt_int_t* objective_sense_ptr)
+{
+  PROBLEM_OR_FAIL(objective_sense_ptr);
+  *objective_sense_ptr = p.maximize ? CUOPT_MAXIMIZE : CUOPT_MINIMIZE;
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetObjectiveOffset(cuOptOptimizationProblem problem, cuopt_float_t* objective_offset_ptr)
+{
+  PROBLEM_OR_FAIL(objective_offset_ptr);
+  *objective_offset_ptr = p.objective_offset;
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetObjectiveCoefficients(cuOptOptimizationProblem problem, cuopt_float_t* objective_coefficients_ptr)
+{
+  PROBLEM_OR_FAIL(objective_coefficients_ptr);
+  copy_out(objective_coefficients_ptr, p.objective_coefficients);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetNumNonZeros(cuOptOptimizationProblem problem, cuopt_int_t* num_non_zeros_ptr)
+{
+  PROBLEM_OR_FAIL(num_non_zeros_ptr);
+  *num_non_zeros_ptr = p.nnz();
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetConstraintMatrix(cuOptOptimizationProblem problem,
+                                     cuopt_int_t* constraint_matrix_row_offsets_ptr,
+                                     cuopt_int_t* constraint_matrix_column_indices_ptr,
+                                     cuopt_float_t* constraint_matrix_coefficients_ptr)
+{
+  PROBLEM_OR_FAIL(constraint_matrix_row_offsets_ptr);
+  if (constraint_matrix_column_indices_ptr == nullptr || constraint_matrix_coefficients_ptr == nullptr)
+    return CUOPT_INVALID_ARGUMENT;
+  copy_out(constraint_matrix_row_offsets_ptr, p.A_offsets);
+  copy_out(constraint_matrix_column_indices_ptr, p.A_indices);
+  copy_out(constraint_matrix_coefficients_ptr, p.A_values);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetConstraintSense(cuOptOptimizationProblem problem, char* constraint_sense_ptr)
+{
+  PROBLEM_OR_FAIL(constraint_sense_ptr);
+  copy_out(constraint_sense_ptr, p.row_types);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetConstraintRightHandSide(cuOptOptimizationProblem problem, cuopt_float_t* rhs_ptr)
+{
+  PROBLEM_OR_FAIL(rhs_ptr);
+  copy_out(rhs_ptr, p.constraint_bounds);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetConstraintLowerBounds(cuOptOptimizationProblem problem, cuopt_float_t* lower_bounds_ptr)
+{
+  PROBLEM_OR_FAIL(lower_bounds_ptr);
+  copy_out(lower_bounds_ptr, p.constraint_lower_bounds);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetConstraintUpperBounds(cuOptOptimizationProblem problem, cuopt_float_t* upper_bounds_ptr)
+{
+  PROBLEM_OR_FAIL(upper_bounds_ptr);
+  copy_out(upper_bounds_ptr, p.constraint_upper_bounds);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetVariableLowerBounds(cuOptOptimizationProblem problem, cuopt_float_t* lower_bounds_ptr)
+{
+  PROBLEM_OR_FAIL(lower_bounds_ptr);
+  copy_out(lower_bounds_ptr, p.variable_lower_bounds);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetVariableUpperBounds(cuOptOptimizationProblem problem, cuopt_float_t* upper_bounds_ptr)
+{
+  PROBLEM_OR_FAIL(upper_bounds_ptr);
+  copy_out(upper_bounds_ptr, p.variable_upper_bounds);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetVariableTypes(cuOptOptimizationProblem problem, char* variable_types_ptr)
+{
+  PROBLEM_OR_FAIL(variable_types_ptr);
+  for (size_t j = 0; j < p.variable_types.size(); ++j)
+    variable_types_ptr[j] = p.variable_types[j] == 'I' ? CUOPT_INTEGER : CUOPT_CONTINUOUS;
+  return CUOPT_SUCCESS;
+}
+
+cuopt_int_t cuOptCreateSolverSettings(cuOptSolverSettings* settings_ptr)
+{
+  if (settings_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  *settings_ptr = new (std::nothrow) solver_settings_t();
+  return *settings_ptr ? CUOPT_SUCCESS : CUOPT_OUT_OF_MEMORY;
+}
+void cuOptDestroySolverSettings(cuOptSolverSettings* settings_ptr)
+{
+  if (settings_ptr == nullptr) return;
+  delete static_cast<solver_settings_t*>(*settings_ptr);
+  *settings_ptr = nullptr;
+}
+
+cuopt_int_t cuOptSetParameter(cuOptSolverSettings settings, const char* parameter_name, const char* parameter_value)
+{
+  if (settings == nullptr || parameter_name == nullptr || parameter_value == nullptr) return CUOPT_INVALID_ARGUMENT;
+  try {
+    static_cast<solver_settings_t*>(settings)->set_from_string(parameter_name, parameter_value);
+  } catch (const std::exception&) {
+    return CUOPT_INVALID_ARGUMENT;
+  }
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetParameter(cuOptSolverSettings settings,
+                              const char* parameter_name,
+                              cuopt_int_t parameter_value_size,
+                              char* parameter_value)
+{
+  if (settings == nullptr || parameter_name == nullptr || parameter_value == nullptr || parameter_value_size <= 0)
+    return CUOPT_INVALID_ARGUMENT;
+  try {
+    const std::string s = static_cast<solver_settings_t*>(settings)->get_as_string(parameter_name);
+    std::snprintf(parameter_value, parameter_value_size, "%s", s.c_str());
+  } catch (const std::exception&) {
+    return CUOPT_INVALID_ARGUMENT;
+  }
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptSetIntegerParameter(cuOptSolverSettings settings, const char* parameter_name, cuopt_int_t parameter_value)
+{
+  if (settings == nullptr || parameter_name == nullptr) return CUOPT_INVALID_ARGUMENT;
+  try {
+    static_cast<solver_settings_t*>(settings)->set_int(parameter_name, parameter_value);
+  } catch (const std::exception&) {
+    return CUOPT_INVALID_ARGUMENT;
+  }
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetIntegerParameter(cuOptSolverSettings settings, const char* parameter_name, cuopt_int_t* parameter_value)
+{
+  if (settings == nullptr || parameter_name == nullptr || parameter_value == nullptr) return CUOPT_INVALID_ARGUMENT;
+  try {
+    *parameter_value = static_cast<solver_settings_t*>(settings)->get_int(parameter_name);
+  } catch (const std::exception&) {
+    return CUOPT_INVALID_ARGUMENT;
+  }
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptSetFloatParameter(cuOptSolverSettings settings, const char* parameter_name, cuopt_float_t parameter_value)
+{
+  if (settings == nullptr || parameter_name == nullptr) return CUOPT_INVALID_ARGUMENT;
+  try {
+    static_cast<solver_settings_t*>(settings)->set_float(parameter_name, parameter_value);
+  } catch (const std::exception&) {
+    return CUOPT_INVALID_ARGUMENT;
+  }
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetFloatParameter(cuOptSolverSettings settings, const char* parameter_name, cuopt_float_t* parameter_value)
+{
+  if (settings == nullptr || parameter_name == nullptr || parameter_value == nullptr) return CUOPT_INVALID_ARGUMENT;
+  try {
+    *parameter_value = static_cast<solver_settings_t*>(settings)->get_float(parameter_name);
+  } catch (const std::exception&) {
+    return CUOPT_INVALID_ARGUMENT;
+  }
+  return CUOPT_SUCCESS;
+}
+
+cuopt_int_t cuOptIsMIP(cuOptOptimizationProblem problem, cuopt_int_t* is_mip_ptr)
+{
+  PROBLEM_OR_FAIL(is_mip_ptr);
+  *is_mip_ptr = p.is_mip() ? 1 : 0;
+  return CUOPT_SUCCESS;
+}
+
+cuopt_int_t cuOptSolve(cuOptOptimizationProblem problem, cuOptSolverSettings settings, cuOptSolution* solution_ptr)
+{
+  if (problem == nullptr || settings == nullptr || solution_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  const lp_problem_t& p       = *static_cast<const lp_problem_t*>(problem);
+  const solver_settings_t& ss = *static_cast<const solver_settings_t*>(settings);
+  auto* h                     = new (std::nothrow) solution_handle_t();
+  if (!h) return CUOPT_OUT_OF_MEMORY;
+  if (p.is_mip()) {
+    // LP-only build: answer with an error solution instead of a MIP search
+    h->is_mip            = false;
+    h->sol.error_status  = CUOPT_VALIDATION_ERROR;
+    h->sol.error_message = "cuopt-b200 implements the LP (PDLP) path only; the problem declares integer variables";
+  } else {
+    // method Concurrent / DualSimplex / PDLP all run PDLP here; crossover is not part of this build
+    h->sol = solve_lp(p, ss.pdlp());
+    if (h->sol.error_status == 0) log_solution(ss.pdlp(), p, h->sol);
+  }
+  *solution_ptr = h;
+  return h->sol.error_status;
+}
+
+void cuOptDestroySolution(cuOptSolution* solution_ptr)
+{
+  if (solution_ptr == nullptr || *solution_ptr == nullptr) return;
+  delete static_cast<solution_handle_t*>(*solution_ptr);
+  *solution_ptr = nullptr;
+}
+
+#define SOLUTION_OR_FAIL(out)                                               \
+  if (solution == nullptr || (out) == nullptr) return CUOPT_INVALID_ARGUMENT; \
+  const solution_handle_t& s = *static_cast<const solution_handle_t*>(solution)
+
+cuopt_int_t cuOptGetTerminationStatus(cuOptSolution solution, cuopt_int_t* termination_status_ptr)
+{
+  SOLUTION_OR_FAIL(termination_status_ptr);
+  *termination_status_ptr = (cuopt_int_t)s.sol.termination_status;
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetErrorStatus(cuOptSolution solution, cuopt_int_t* error_status_ptr)
+{
+  SOLUTION_OR_FAIL(error_status_ptr);
+  *error_status_ptr = s.sol.error_status;
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetErrorString(cuOptSolution solution, char* error_string_ptr, cuopt_int_t error_string_size)
+{
+  SOLUTION_OR_FAIL(error_string_ptr);
+  if (error_string_size > 0) std::snprintf(error_string_ptr, error_string_size, "%s", s.sol.error_message.c_str());
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetPrimalSolution(cuOptSolution solution, cuopt_float_t* solution_values)
+{
+  SOLUTION_OR_FAIL(solution_values);
+  copy_out(solution_values, s.sol.primal);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetObjectiveValue(cuOptSolution solution, cuopt_float_t* objective_value_ptr)
+{
+  SOLUTION_OR_FAIL(objective_value_ptr);
+  *objective_value_ptr = s.sol.stats.primal_objective;  // solver_solution.cu:307-310
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetSolveTime(cuOptSolution solution, cuopt_float_t* solve_time_ptr)
+{
+  SOLUTION_OR_FAIL(solve_time_ptr);
+  *solve_time_ptr = s.sol.stats.solve_time;
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetMIPGap(cuOptSolution solution, cuopt_float_t* mip_gap_ptr)
+{
+  SOLUTION_OR_FAIL(mip_gap_ptr);
+  (void)s;
+  return CUOPT_INVALID_ARGUMENT;  // LP solution (cuopt_c.cpp:776-779)
+}
+cuopt_int_t cuOptGetSolutionBound(cuOptSolution solution, cuopt_float_t* solution_bound_ptr)
+{
+  SOLUTION_OR_FAIL(solution_bound_ptr);
+  (void)s;
+  return CUOPT_INVALID_ARGUMENT;
+}
+cuopt_int_t cuOptGetDualSolution(cuOptSolution solution, cuopt_float_t* dual_solution_ptr)
+{
+  SOLUTION_OR_FAIL(dual_solution_ptr);
+  copy_out(dual_solution_ptr, s.sol.dual);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptGetReducedCosts(cuOptSolution solution, cuopt_float_t* reduced_cost_ptr)
+{
+  SOLUTION_OR_FAIL(reduced_cost_ptr);
+  copy_out(reduced_cost_ptr, s.sol.reduced_cost);
+  return CUOPT_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------ extension
+static void export_stats(const lp_stats_t& t, cuOptB200LPStats* o)
+{
+  std::memset(o, 0, sizeof(*o));
+  o->number_of_steps_taken           = t.number_of_steps_taken;
+  o->total_number_of_attempted_steps = t.total_number_of_attempted_steps;
+  o->l2_primal_residual              = t.l2_primal_residual;
+  o->l2_relative_primal_residual     = t.l2_relative_primal_residual;
+  o->l2_dual_residual                = t.l2_dual_residual;
+  o->l2_relative_dual_residual       = t.l2_relative_dual_residual;
+  o->primal_objective                = t.primal_objective;
+  o->dual_objective                  = t.dual_objective;
+  o->gap                             = t.gap;
+  o->relative_gap                    = t.relative_gap;
+  o->solved_by_pdlp                  = t.solved_by_pdlp;
+  o->n_major_iterations              = t.n_major_iterations;
+  o->n_restarts                      = t.n_restarts;
+  o->solve_time                      = t.solve_time;
+  o->setup_seconds                   = t.setup_seconds;
+  o->pdhg_loop_seconds               = t.pdhg_loop_seconds;
+  o->termination_seconds             = t.termination_seconds;
+  o->initial_step_size               = t.initial_step_size;
+  o->initial_primal_weight           = t.initial_primal_weight;
+  o->final_step_size                 = t.final_step_size;
+  o->final_primal_weight             = t.final_primal_weight;
+  o->kernel_launches                 = t.kernel_launches;
+}
+
+cuopt_int_t cuOptB200GetLPStats(cuOptSolution solution, cuOptB200LPStats* stats)
+{
+  SOLUTION_OR_FAIL(stats);
+  export_stats(s.sol.stats, stats);
+  return CUOPT_SUCCESS;
+}
+
+cuopt_int_t cuOptB200SolverCreate(cuOptOptimizationProblem problem, cuOptSolverSettings settings, cuOptB200Solver* solver_ptr)
+{
+  if (problem == nullptr || settings == nullptr || solver_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  *solver_ptr = nullptr;
+  try {
+    auto h    = std::make_unique<solver_handle_t>();
+    h->solver = std::make_unique<pdlp_solver_t>(*static_cast<const lp_problem_t*>(problem),
+                                                static_cast<const solver_settings_t*>(settings)->pdlp());
+    *solver_ptr = h.release();
+  } catch (const lp_error& e) {
+    std::fprintf(stderr, "cuOptB200SolverCreate: %s\n", e.what());
+    return e.type == error_type_t::Success ? CUOPT_VALIDATION_ERROR : (cuopt_int_t)e.type;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "cuOptB200SolverCreate: %s\n", e.what());
+    return CUOPT_RUNTIME_ERROR;
+  }
+  return CUOPT_SUCCESS;
+}
+void cuOptB200SolverDestroy(cuOptB200Solver* solver_ptr)
+{
+  if (solver_ptr == nullptr || *solver_ptr == nullptr) return;
+  delete static_cast<solver_handle_t*>(*solver_ptr);
+  *solver_ptr = nullptr;
+}
+
+#define SOLVER_GUARD(expr)                                     \
+  try {                                                        \
+    expr;                                                      \
+  } catch (const lp_error& e) {                                \
+    std::fprintf(stderr, "cuopt-b200: %s\n", e.what());        \
+    return (cuopt_int_t)e.type;                                \
+  } catch (const std::exception& e) {                          \
+    std::fprintf(stderr, "cuopt-b200: %s\n", e.what());        \
+    return CUOPT_RUNTIME_ERROR;                                \
+  }
+
+cuopt_int_t cuOptB200SolverInitialise(cuOptB200Solver solver)
+{
+  if (solver == nullptr) return CUOPT_INVALID_ARGUMENT;
+  SOLVER_GUARD(static_cast<solver_handle_t*>(solver)->solver->initialise());
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptB200SolverAdvance(cuOptB200Solver solver, cuopt_int_t accepted_steps, cuopt_int_t* finished_ptr)
+{
+  if (solver == nullptr) return CUOPT_INVALID_ARGUMENT;
+  auto* h = static_cast<solver_handle_t*>(solver);
+  SOLVER_GUARD(h->finished = h->solver->advance(accepted_steps));
+  if (finished_ptr) *finished_ptr = h->finished ? 1 : 0;
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptB200SolverGetScalar(cuOptB200Solver solver, const char* name, cuopt_float_t* value_ptr)
+{
+  if (solver == nullptr || name == nullptr || value_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  SOLVER_GUARD(*value_ptr = static_cast<solver_handle_t*>(solver)->solver->scalar(name));
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptB200SolverGetVector(cuOptB200Solver solver,
+                                     const char* name,
+                                     cuopt_float_t* values,
+                                     cuopt_int_t capacity,
+                                     cuopt_int_t* size_ptr)
+{
+  if (solver == nullptr || name == nullptr) return CUOPT_INVALID_ARGUMENT;
+  SOLVER_GUARD({
+    auto v = static_cast<solver_handle_t*>(solver)->solver->vector(name);
+    if (size_ptr) *size_ptr = (cuopt_int_t)v.size();
+    if (values) {
+      if ((size_t)capacity < v.size()) return CUOPT_INVALID_ARGUMENT;
+      copy_out(values, v);
+    }
+  });
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptB200SolverGetSolution(cuOptB200Solver solver, cuOptSolution* solution_ptr)
+{
+  if (solver == nullptr || solution_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  auto* h   = static_cast<solver_handle_t*>(solver);
+  auto* out = new (std::nothrow) solution_handle_t();
+  if (!out) return CUOPT_OUT_OF_MEMORY;
+  out->sol      = h->solver->solution();
+  *solution_ptr = out;
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptB200SolverProfileKernels(cuOptB200Solver solver,
+                                          cuopt_int_t warmup_steps,
+                                          cuopt_int_t reps,
+                                          cuOptB200KernelProfile* profile)
+{
+  if (solver == nullptr || profile == nullptr || reps <= 0) return CUOPT_INVALID_ARGUMENT;
+  SOLVER_GUARD({
+    const kernel_profile_t k      = static_cast<solver_handle_t*>(solver)->solver->profile_kernels(warmup_steps, reps);
+    profile->ms_primal_step       = k.ms_primal_step;
+    profile->ms_dual_step         = k.ms_dual_step;
+    profile->ms_transpose_step    = k.ms_transpose_step;
+    profile->bytes_primal_step    = k.bytes_primal_step;
+    profile->bytes_dual_step      = k.bytes_dual_step;
+    profile->bytes_transpose_step = k.bytes_transpose_step;
+    profile->ms_iteration         = k.ms_iteration;
+    profile->reps                 = k.reps;
+    profile->grid_primal          = k.grid_primal;
+    profile->grid_dual            = k.grid_dual;
+    profile->grid_transpose       = k.grid_transpose;
+  });
+  return CUOPT_SUCCESS;
+}
+
+cuopt_int_t cuOptB200ReadProblem(const char* filename, cuopt_int_t fixed_format, cuOptOptimizationProblem* problem_ptr)
+{
+  if (filename == nullptr || problem_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  *problem_ptr = nullptr;
+  try {
+    *problem_ptr = new lp_problem_t(read_mps(filename, fixed_format != 0));
+    return CUOPT_SUCCESS;
+  } catch (const lp_error& e) {
+    return e.type == error_type_t::MpsFileError ? CUOPT_MPS_FILE_ERROR : CUOPT_MPS_PARSE_ERROR;
+  } catch (const std::exception&) {
+    return CUOPT_MPS_PARSE_ERROR;
+  }
+}
+
+const char* cuOptB200Version(void) { return "cuopt-b200 0.1.0 sm_100a"; }
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// Small CUDA helpers for the PDLP solver: error checking, RAII device buffers,
+// deterministic block reductions and cache-hinted loads.  sm_100a only.
+#pragma once
+
+#include "lp_problem.hpp"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace cuopt_b200 {
+
+#define CUOPT_CUDA_TRY(call)                                                                              \
+  do {                                                                                                    \
+    cudaError_t err__ = (call);                                                                           \
+    if (err__ != cudaSuccess) {                                                                           \
+      cudaGetLastError();                                                                                 \
+      throw ::cuopt_b200::lp_error(                                                                       \
+        err__ == cudaErrorMemoryAllocation ? ::cuopt_b200::error_type_t::OutOfMemory                      \
+                                           : ::cuopt_b200::error_type_t::RuntimeError,                    \
+        std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " + __FILE__ + ":" +               \
+          std::to_string(__LINE__));                                                                      \
+    }                                                                                                     \
+  } while (0)
+
+// Device array with value semantics disabled; memory comes straight from cudaMalloc
+// (one allocation per vector, sized once per solve: no pool needed at 180 GB HBM).
+template <typename T>
+class dvec {
+ public:
+  dvec() = default;
+  explicit dvec(size_t n) { resize(n); }
+  dvec(const dvec&)            = delete;
+  dvec& operator=(const dvec&) = delete;
+  dvec(dvec&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  dvec& operator=(dvec&& o) noexcept
+  {
+    if (this != &o) { release(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+    return *this;
+  }
+  ~dvec() { release(); }
+  void resize(size_t n)
+  {
+    release();
+    n_ = n;
+    if (n) CUOPT_CUDA_TRY(cudaMalloc(&p_, std::max<size_t>(n, 1) * sizeof(T)));
+  }
+  void release()
+  {
+    if (p_) cudaFree(p_);
+    p_ = nullptr;
+    n_ = 0;
+  }
+  void upload(const T* h, size_t n, cudaStream_t s)
+  {
+    if (n_ != n) resize(n);
+    if (n) CUOPT_CUDA_TRY(cudaMemcpyAsync(p_, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+  void download(T* h, cudaStream_t s) const
+  {
+    if (n_) CUOPT_CUDA_TRY(cudaMemcpyAsync(h, p_, n_ * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+  void zero(cudaStream_t s)
+  {
+    if (n_) CUOPT_CUDA_TRY(cudaMemsetAsync(p_, 0, n_ * sizeof(T), s));
+  }
+  void copy_from(const dvec& o, cudaStream_t s)
+  {
+    if (n_ != o.n_) resize(o.n_);
+    if (n_) CUOPT_CUDA_TRY(cudaMemcpyAsync(p_, o.p_, n_ * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  }
+  T* data() { return p_; }
+  const T* data() const { return p_; }
+  size_t size() const { return n_; }
+
+ private:
+  T* p_     = nullptr;
+  size_t n_ = 0;
+};
+
+// ---- device-side helpers ---------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Fixed-shape tree: xor-shuffle inside each warp, then the first warp folds the per-warp values.
+// The result is identical run to run for a given blockDim.  `scratch` holds >= 32 doubles.
+// All threads receive the result.
+template <bool IsMax = false>
+__device__ __forceinline__ double block_reduce(double v, double* scratch)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = IsMax ? warp_max(v) : warp_sum(v);
+  __syncthreads();  // protect scratch from a previous use
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  double r = (lane < nw) ? scratch[lane] : 0.0;
+  r        = IsMax ? warp_max(r) : warp_sum(r);
+  return r;
+}
+
+// Streaming (read-once) loads: keep them from displacing the gathered vector in L1/L2.
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+
+}  // namespace cuopt_b200

@@ -97,6 +97,11 @@ struct reader_t {
       static const size_t len[6] = {2, 8, 8, 12, 8, 12};
       for (int i = 0; i < 6; ++i)
         f.push_back(trim(slice(line, pos[i], len[i])));
+      // the second (name, value) pair counts only when something lies beyond column 40, exactly the
+      // reference's test `line.find_last_not_of(" \r\t\n") > 39` (mps_parser.cpp:603, :692, :881): a first
+      // value wider than its 12-character field must not be mistaken for a second pair
+      const auto last = line.find_last_not_of(" \t\r\n");
+      if (last == std::string_view::npos || last <= 39) f.resize(4);
       while (!f.empty() && f.back().empty())
         f.pop_back();
     }

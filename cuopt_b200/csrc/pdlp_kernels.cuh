@@ -1,0 +1,721 @@
+// Hand-written sm_100a kernels of the PDLP hot path.
+//
+// One PDHG attempt = three launches (K1 primal step, K2 A*xbar + dual step,
+// K3 A^T*y' + interaction/movement reductions + step-size rule), replacing the
+// reference's per-iteration sequence of 2 cusparseSpMV + 4 cub::DeviceTransform +
+// 3 cublasDdot + 1 scalar kernel + host sync
+// (cpp/src/linear_programming/pdhg.cu:73-216,
+//  step_size_strategy/adaptive_step_size_strategy.cu:92-345,
+//  restart_strategy/weighted_average_solution.cu:73-110).
+// Accept/reject, the step-size update, the weighted-average accumulation and the
+// x<->x' buffer swap all happen on the device (control block pdhg_ctl_t), so a
+// whole batch of attempts runs without the host.
+//
+// SpMV scheme ("row blocks"): the host cuts the CSR rows into consecutive blocks of
+// at most SPMV_NNZ nonzeros; a CTA streams a block's (col,val) entries with
+// coalesced evict-first loads, gathers the vector, parks the products in shared
+// memory (padded against bank conflicts) and then one thread per row adds that
+// row's products left to right and runs the fused row epilogue.  Matrix bytes are
+// read exactly once per pass; reductions use fixed-shape trees and a fixed grid,
+// so results are bit-reproducible run to run.
+#pragma once
+
+#include "device_utils.cuh"
+
+#include <math_constants.h>
+
+namespace cuopt_b200 {
+
+constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_NNZ     = 2048;  // nonzeros per row block (8 per thread)
+constexpr int SPMV_ROWS    = 2048;  // max rows per row block
+constexpr int SPMV_PADDED  = SPMV_NNZ + (SPMV_NNZ >> 3);
+__host__ __device__ constexpr int spmv_pad(int e) { return e + (e >> 3); }
+
+constexpr int EW_THREADS = 256;  // element-wise kernels
+
+struct csr_view_t {
+  int rows;
+  const int* off;
+  const int* idx;
+  const double* val;
+  int n_blocks;
+  const int4* blk;  // {first row, one-past-last row, first nnz, one-past-last nnz}
+};
+
+// Device-resident control block: every scalar the PDHG loop reads or writes.
+struct pdhg_ctl_t {
+  double step_size, primal_weight, tau, sigma;
+  double pending_weight;  // weight of the accepted-but-not-yet-averaged iterate
+  double sum_weights;     // sum of averaging weights since the last restart
+  double interaction, norm_dx2, norm_dy2;
+  double reduction_exponent, growth_exponent, primal_smoothing, dual_smoothing;
+  int parity;       // which of the two (x, y, A^T y) buffer sets is "current"
+  int pending_avg;  // buffers[parity] hold an accepted iterate that still has to enter the running sums
+  int active;       // 0 -> remaining launches of the batch are no-ops
+  int valid;        // last attempt: 1 accepted, 0 rejected, -1 numerical error
+  int k_pdhg;       // attempts with a sane movement (reference: d_total_pdhg_iterations_)
+  int attempts;     // all attempts (reference: total_pdhg_iterations_ on the host)
+  int accepted;     // accepted steps (reference: internal_solver_iterations_)
+  int target;       // the batch stops once `accepted` reaches this
+  int its_since_restart;
+  unsigned ticket[4];
+};
+
+// Result of one termination evaluation (termination_strategy/convergence_information.cu).
+struct eval_t {
+  double l2_primal_residual, l2_dual_residual, primal_objective, dual_objective, gap, abs_objective, kkt;
+  double l2_primal_variable, l2_dual_variable;
+  int status;  // termination_status_t; 6 (NumericalError) == "keep going" as in termination_strategy.cu:186
+  int pad;
+};
+
+struct eval_consts_t {
+  double objective_scaling_factor, objective_offset;
+  double abs_gap_tol, rel_gap_tol, abs_primal_tol, rel_primal_tol, abs_dual_tol, rel_dual_tol;
+  double l2_norm_b, l2_norm_c;
+  int reduced_cost_rule;  // 1: handle_some_primal_gradients_on_finite_bounds_as_residuals
+};
+
+// ---------------------------------------------------------------------------------------------
+// Row-block SpMV core.  NV vectors are multiplied in the same pass over the matrix.
+// row_op(row, sums[NV]) is called exactly once per row of the block by one thread.
+// `prod` is NV x SPMV_PADDED doubles of shared memory, `red` >= 32 doubles.
+// ---------------------------------------------------------------------------------------------
+template <int NV, typename RowOp>
+__device__ __forceinline__ void spmv_row_block(const csr_view_t& A,
+                                               const int4 d,
+                                               const double* const* x,
+                                               double* prod,
+                                               double* red,
+                                               RowOp& row_op)
+{
+  const int tid = threadIdx.x;
+  const int r0 = d.x, r1 = d.y, lo = d.z, hi = d.w;
+  if (hi - lo > SPMV_NNZ) {
+    // one long row: strided partial sums, then the fixed block tree
+    double acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+    for (int e = lo + tid; e < hi; e += SPMV_THREADS) {
+      const int c    = ld_stream(A.idx + e);
+      const double a = ld_stream(A.val + e);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] += a * __ldg(x[v] + c);
+    }
+    double s[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s[v] = block_reduce(acc[v], red);
+    if (tid == 0) row_op(r0, s);
+    __syncthreads();
+    return;
+  }
+  // row extents first: their latency overlaps the staging phase
+  int rs[SPMV_ROWS / SPMV_THREADS], re[SPMV_ROWS / SPMV_THREADS];
+#pragma unroll
+  for (int k = 0; k < SPMV_ROWS / SPMV_THREADS; ++k) {
+    const int r = r0 + tid + k * SPMV_THREADS;
+    if (r < r1) {
+      rs[k] = __ldg(A.off + r) - lo;
+      re[k] = __ldg(A.off + r + 1) - lo;
+    }
+  }
+  // stage products: all index loads, then all value loads + gathers (8 independent chains per thread)
+  int col[SPMV_NNZ / SPMV_THREADS];
+  double a[SPMV_NNZ / SPMV_THREADS];
+#pragma unroll
+  for (int k = 0; k < SPMV_NNZ / SPMV_THREADS; ++k) {
+    const int e = lo + tid + k * SPMV_THREADS;
+    col[k]      = (e < hi) ? ld_stream(A.idx + e) : -1;
+  }
+#pragma unroll
+  for (int k = 0; k < SPMV_NNZ / SPMV_THREADS; ++k) {
+    const int e = lo + tid + k * SPMV_THREADS;
+    a[k]        = (e < hi) ? ld_stream(A.val + e) : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < SPMV_NNZ / SPMV_THREADS; ++k) {
+    if (col[k] >= 0) {
+      const int p = spmv_pad(tid + k * SPMV_THREADS);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) prod[v * SPMV_PADDED + p] = a[k] * __ldg(x[v] + col[k]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < SPMV_ROWS / SPMV_THREADS; ++k) {
+    const int r = r0 + tid + k * SPMV_THREADS;
+    if (r < r1) {
+      double s[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) s[v] = 0.0;
+      for (int p = rs[k]; p < re[k]; ++p) {
+        const int q = spmv_pad(p);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s[v] += prod[v * SPMV_PADDED + q];
+      }
+      row_op(r, s);
+    }
+  }
+  __syncthreads();
+}
+
+// Publish per-CTA partial sums and elect the last CTA to finish (returns true in every thread of
+// that CTA).  `parts` is NQ x gridDim.x doubles; the elected CTA reads them back in a fixed order.
+template <int NQ>
+__device__ __forceinline__ bool publish_and_elect(const double (&local)[NQ], double* parts, unsigned* ticket, double* red)
+{
+  __shared__ bool is_last;
+  double tot[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) tot[q] = block_reduce(local[q], red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) parts[q * gridDim.x + blockIdx.x] = tot[q];
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    is_last          = (t == gridDim.x - 1);
+    if (is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// Sum `count` published partials (written by other CTAs) in a fixed order; result in all threads.
+__device__ __forceinline__ double gather_partials(const double* parts, int count, double* red)
+{
+  double s = 0.0;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) s += __ldcg(parts + i);
+  return block_reduce(s, red);
+}
+
+// =============================================================================================
+// K1 — primal step.  x' = clamp(x - tau (c - A^T y), l, u), xbar = 2x' - x
+// (pdhg.cu:137-158 + utils.cuh:81-95), fused with the primal half of the running-average update
+// of the PREVIOUS accepted step (weighted_average_solution.cu:88-94).
+// Algorithmic bytes per variable: read x, c, A^T y, l, u (+ sum_x r/w when pending) ; write x', xbar.
+// =============================================================================================
+__global__ void __launch_bounds__(EW_THREADS) k_primal_step(const pdhg_ctl_t* __restrict__ ctl,
+                                                            int n,
+                                                            double* __restrict__ xbuf0,
+                                                            double* __restrict__ xbuf1,
+                                                            const double* __restrict__ aty0,
+                                                            const double* __restrict__ aty1,
+                                                            const double* __restrict__ c,
+                                                            const double* __restrict__ l,
+                                                            const double* __restrict__ u,
+                                                            double* __restrict__ sum_x,
+                                                            double* __restrict__ xbar)
+{
+  if (!ctl->active) return;
+  const int cur           = ctl->parity;
+  const double* x         = cur ? xbuf1 : xbuf0;
+  double* xn              = cur ? xbuf0 : xbuf1;
+  const double* aty       = cur ? aty1 : aty0;
+  const double tau        = ctl->tau;
+  const bool pending      = ctl->pending_avg != 0;
+  const double w          = ctl->pending_weight;
+  const int stride        = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double xj = x[j];
+    if (pending) sum_x[j] = sum_x[j] + w * xj;
+    const double gradient = ld_stream(c + j) - aty[j];
+    double next           = xj - (tau * gradient);
+    next                  = fmax(fmin(next, ld_stream(u + j)), ld_stream(l + j));
+    xn[j]                 = next;
+    xbar[j]               = next - xj + next;
+  }
+}
+
+// =============================================================================================
+// K2 — A*xbar and dual step.  y' = max(ybar + sigma lc, min(ybar + sigma uc, 0)), ybar = y - sigma (A xbar)
+// (pdhg.cu:73-117 + utils.cuh:98-112) + dual half of the running average + partial ||dy||^2.
+// =============================================================================================
+__global__ void __launch_bounds__(SPMV_THREADS) k_dual_step(const pdhg_ctl_t* __restrict__ ctl,
+                                                            csr_view_t A,
+                                                            const double* __restrict__ xbar,
+                                                            double* __restrict__ ybuf0,
+                                                            double* __restrict__ ybuf1,
+                                                            const double* __restrict__ lc,
+                                                            const double* __restrict__ uc,
+                                                            double* __restrict__ sum_y,
+                                                            double* __restrict__ part_dy2)
+{
+  if (!ctl->active) return;
+  __shared__ double prod[SPMV_PADDED];
+  __shared__ double red[32];
+  const int cur      = ctl->parity;
+  const double* y    = cur ? ybuf1 : ybuf0;
+  double* yn         = cur ? ybuf0 : ybuf1;
+  const double sigma = ctl->sigma;
+  const bool pending = ctl->pending_avg != 0;
+  const double w     = ctl->pending_weight;
+  double dy2         = 0.0;
+  auto row_op        = [&](int i, const double (&s)[1]) {
+    const double yi = y[i];
+    if (pending) sum_y[i] = sum_y[i] + w * yi;
+    double next      = yi - (sigma * s[0]);
+    const double low = next + sigma * ld_stream(lc + i);
+    const double up  = next + sigma * ld_stream(uc + i);
+    next             = fmax(low, fmin(up, 0.0));
+    yn[i]            = next;
+    const double d   = next - yi;
+    dy2 += d * d;
+  };
+  const double* xs[1] = {xbar};
+  for (int b = blockIdx.x; b < A.n_blocks; b += gridDim.x)
+    spmv_row_block<1>(A, __ldg(A.blk + b), xs, prod, red, row_op);
+  const double tot = block_reduce(dy2, red);
+  if (threadIdx.x == 0) part_dy2[blockIdx.x] = tot;
+}
+
+// =============================================================================================
+// K3 — A^T*y' with the interaction / movement reductions and, in the last CTA to finish, the
+// adaptive step-size rule with accept/reject (adaptive_step_size_strategy.cu:92-188, 232-345).
+// interaction = dx . (A^T y' - A^T y)  (the reference's SpMV-saving form, :267-277).
+// =============================================================================================
+__global__ void __launch_bounds__(SPMV_THREADS) k_transpose_step(pdhg_ctl_t* __restrict__ ctl,
+                                                                 csr_view_t AT,
+                                                                 const double* __restrict__ ybuf0,
+                                                                 const double* __restrict__ ybuf1,
+                                                                 const double* __restrict__ xbuf0,
+                                                                 const double* __restrict__ xbuf1,
+                                                                 double* __restrict__ aty0,
+                                                                 double* __restrict__ aty1,
+                                                                 double* __restrict__ parts,  // 2 x gridDim.x
+                                                                 const double* __restrict__ part_dy2,
+                                                                 int n_part_dy2)
+{
+  if (!ctl->active) return;
+  __shared__ double prod[SPMV_PADDED];
+  __shared__ double red[32];
+  const int cur     = ctl->parity;
+  const double* yn  = cur ? ybuf0 : ybuf1;  // candidate y'
+  const double* x   = cur ? xbuf1 : xbuf0;
+  const double* xn  = cur ? xbuf0 : xbuf1;
+  const double* aty = cur ? aty1 : aty0;
+  double* atyn      = cur ? aty0 : aty1;
+  double acc[2]     = {0.0, 0.0};  // interaction, ||dx||^2
+  auto row_op       = [&](int j, const double (&s)[1]) {
+    atyn[j]        = s[0];
+    const double d = xn[j] - x[j];
+    acc[0] += d * (s[0] - aty[j]);
+    acc[1] += d * d;
+  };
+  const double* ys[1] = {yn};
+  for (int b = blockIdx.x; b < AT.n_blocks; b += gridDim.x)
+    spmv_row_block<1>(AT, __ldg(AT.blk + b), ys, prod, red, row_op);
+
+  if (!publish_and_elect<2>(acc, parts, &ctl->ticket[0], red)) return;
+  const double interaction = gather_partials(parts, gridDim.x, red);
+  const double dx2         = gather_partials(parts + gridDim.x, gridDim.x, red);
+  const double dy2         = gather_partials(part_dy2, n_part_dy2, red);
+  if (threadIdx.x != 0) return;
+
+  pdhg_ctl_t s     = *ctl;
+  s.interaction    = interaction;
+  s.norm_dx2       = dx2;
+  s.norm_dy2       = dy2;
+  s.attempts += 1;
+  const double pw       = s.primal_weight;
+  const double movement = s.primal_smoothing * pw * dx2 + (s.dual_smoothing / pw) * dy2;
+  bool accept;
+  if (movement <= 0.0 || movement >= 1.0e100) {
+    // numerical error (or exact convergence): the reference leaves the retry loop, still averages and
+    // swaps, and lets the next major iteration decide (pdlp.cu:1193-1221, :780-789)
+    s.valid = -1;
+    accept  = true;
+  } else {
+    const double inter = fabs(interaction);
+    s.k_pdhg += 1;
+    const double kc    = (double)s.k_pdhg;
+    const double limit = inter > 0.0 ? movement / inter : CUDART_INF;
+    accept             = s.step_size <= limit;
+    s.valid            = accept ? 1 : 0;
+    const double c1    = (1.0 - pow(kc + 1.0, -s.reduction_exponent)) * limit;
+    const double c2    = (1.0 + pow(kc + 1.0, -s.growth_exponent)) * s.step_size;
+    s.step_size        = fmin(c1, c2);
+    s.tau              = s.step_size / pw;
+    s.sigma            = s.step_size * pw;
+  }
+  if (accept) {
+    s.parity ^= 1;
+    s.pending_avg    = 1;
+    s.pending_weight = s.step_size;  // the already-updated step size (pdlp.cu:1216-1219)
+    s.sum_weights += s.step_size;
+    s.accepted += 1;
+    s.its_since_restart += 1;
+  } else {
+    s.pending_avg = 0;
+  }
+  s.active    = (s.valid != -1 && s.accepted < s.target) ? 1 : 0;
+  s.ticket[0] = 0u;
+  *ctl        = s;
+}
+
+// Applies a still-pending running-average update (end of a batch, before averages are formed).
+__global__ void __launch_bounds__(EW_THREADS) k_flush_average(const pdhg_ctl_t* __restrict__ ctl,
+                                                              int n,
+                                                              const double* __restrict__ xbuf0,
+                                                              const double* __restrict__ xbuf1,
+                                                              double* __restrict__ sum_x,
+                                                              int m,
+                                                              const double* __restrict__ ybuf0,
+                                                              const double* __restrict__ ybuf1,
+                                                              double* __restrict__ sum_y)
+{
+  if (!ctl->pending_avg) return;
+  const int cur    = ctl->parity;
+  const double* x  = cur ? xbuf1 : xbuf0;
+  const double* y  = cur ? ybuf1 : ybuf0;
+  const double w   = ctl->pending_weight;
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) sum_x[j] = sum_x[j] + w * x[j];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) sum_y[i] = sum_y[i] + w * y[i];
+}
+__global__ void k_clear_pending(pdhg_ctl_t* ctl) { ctl->pending_avg = 0; }
+__global__ void k_begin_batch(pdhg_ctl_t* ctl, int steps)
+{
+  ctl->target = ctl->accepted + steps;
+  ctl->active = (steps > 0 && ctl->valid != -1) ? 1 : 0;
+}
+
+// Plain y = A x on the row-block scheme (A^T y after a restart to the average, pdhg.cu:120-134).
+__global__ void __launch_bounds__(SPMV_THREADS) k_spmv(csr_view_t A, const double* __restrict__ x, double* __restrict__ out)
+{
+  __shared__ double prod[SPMV_PADDED];
+  __shared__ double red[32];
+  auto row_op         = [&](int i, const double (&s)[1]) { out[i] = s[0]; };
+  const double* xs[1] = {x};
+  for (int b = blockIdx.x; b < A.n_blocks; b += gridDim.x)
+    spmv_row_block<1>(A, __ldg(A.blk + b), xs, prod, red, row_op);
+}
+
+// =============================================================================================
+// Termination evaluation on the UNSCALED problem, current and average iterate in ONE pass over A and
+// one over A^T (convergence_information.cu:150-422, termination_strategy.cu:117-250).
+// =============================================================================================
+// utils.cuh:205-219
+__device__ __forceinline__ double bound_value_product(double value, double lower, double upper)
+{
+  double bound = 0.0;
+  if (value > 0.0) bound = lower;
+  else if (value < 0.0) bound = upper;
+  return isfinite(bound) ? value * bound : 0.0;
+}
+
+// T1: rows of A.  parts layout: 6 x gridDim.x = {viol^2, y-part of dual objective, ||y||^2} x {cur, avg}
+__global__ void __launch_bounds__(SPMV_THREADS) k_eval_rows(csr_view_t A,
+                                                            const double* __restrict__ x_cur,
+                                                            const double* __restrict__ x_avg,
+                                                            const double* __restrict__ y_cur,
+                                                            const double* __restrict__ y_avg,
+                                                            const double* __restrict__ lc,
+                                                            const double* __restrict__ uc,
+                                                            double* __restrict__ parts)
+{
+  __shared__ double prod[2 * SPMV_PADDED];
+  __shared__ double red[32];
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  auto row_op   = [&](int i, const double (&s)[2]) {
+    const double lo = lc[i], hi = uc[i];
+    const double yv[2] = {y_cur[i], y_avg[i]};
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      // utils.cuh:166-178
+      const double viol = s[v] < lo ? lo - s[v] : (s[v] > hi ? s[v] - hi : 0.0);
+      acc[v] += viol * viol;
+      acc[2 + v] += bound_value_product(yv[v], lo, hi);
+      acc[4 + v] += yv[v] * yv[v];
+    }
+  };
+  const double* xs[2] = {x_cur, x_avg};
+  for (int b = blockIdx.x; b < A.n_blocks; b += gridDim.x)
+    spmv_row_block<2>(A, __ldg(A.blk + b), xs, prod, red, row_op);
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const double t = block_reduce(acc[q], red);
+    if (threadIdx.x == 0) parts[q * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// T2: rows of A^T + final scalars.  parts layout: 8 x gridDim.x =
+// {||g - rc||^2, rc-part of dual objective, c.x, ||x||^2} x {cur, avg}
+__global__ void __launch_bounds__(SPMV_THREADS) k_eval_cols(pdhg_ctl_t* __restrict__ ctl,
+                                                            csr_view_t AT,
+                                                            const double* __restrict__ x_cur,
+                                                            const double* __restrict__ x_avg,
+                                                            const double* __restrict__ y_cur,
+                                                            const double* __restrict__ y_avg,
+                                                            const double* __restrict__ c,
+                                                            const double* __restrict__ l,
+                                                            const double* __restrict__ u,
+                                                            double* __restrict__ rc_cur,
+                                                            double* __restrict__ rc_avg,
+                                                            double* __restrict__ parts,
+                                                            const double* __restrict__ parts_rows,
+                                                            int n_parts_rows,
+                                                            eval_consts_t k,
+                                                            eval_t* __restrict__ out)  // out[0] current, out[1] average
+{
+  __shared__ double prod[2 * SPMV_PADDED];
+  __shared__ double red[32];
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto row_op   = [&](int j, const double (&s)[2]) {
+    const double cj = c[j], lo = l[j], hi = u[j];
+    const double xv[2] = {x_cur[j], x_avg[j]};
+    double* rcs[2]     = {rc_cur, rc_avg};
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const double g     = cj - s[v];
+      const double bound = g > 0.0 ? lo : hi;  // utils.cuh:196-202
+      double rc;
+      if (g == 0.0) rc = g;
+      else if (k.reduced_cost_rule ? (fabs(xv[v] - bound) <= fabs(xv[v])) : isfinite(bound)) rc = g;  // :222-239
+      else rc = 0.0;
+      rcs[v][j]      = rc;
+      const double r = g - rc;
+      acc[v] += r * r;
+      acc[2 + v] += bound_value_product(rc, lo, hi);
+      acc[4 + v] += xv[v] * cj;
+      acc[6 + v] += xv[v] * xv[v];
+    }
+  };
+  const double* ys[2] = {y_cur, y_avg};
+  for (int b = blockIdx.x; b < AT.n_blocks; b += gridDim.x)
+    spmv_row_block<2>(AT, __ldg(AT.blk + b), ys, prod, red, row_op);
+
+  if (!publish_and_elect<8>(acc, parts, &ctl->ticket[1], red)) return;
+  double tot[14];
+  for (int q = 0; q < 8; ++q) tot[q] = gather_partials(parts + q * gridDim.x, gridDim.x, red);
+  for (int q = 0; q < 6; ++q) tot[8 + q] = gather_partials(parts_rows + q * n_parts_rows, n_parts_rows, red);
+  if (threadIdx.x != 0) return;
+  const double pw = ctl->primal_weight;
+  for (int v = 0; v < 2; ++v) {
+    eval_t e;
+    e.l2_primal_residual = sqrt(tot[8 + v]);
+    e.l2_dual_residual   = sqrt(tot[v]);
+    double p             = tot[4 + v];
+    double dobj          = tot[8 + 2 + v] + tot[2 + v];
+    if (k.objective_scaling_factor != 1.0 || k.objective_offset != 0.0) {
+      p    = k.objective_scaling_factor * p + k.objective_offset;
+      dobj = k.objective_scaling_factor * dobj + k.objective_offset;
+    }
+    e.primal_objective   = p;
+    e.dual_objective     = dobj;
+    e.gap                = fabs(p - dobj);
+    e.abs_objective      = fabs(p) + fabs(dobj);
+    e.l2_primal_variable = sqrt(tot[6 + v]);
+    e.l2_dual_variable   = sqrt(tot[8 + 4 + v]);
+    // termination_strategy.cu:117-250 (l2 criteria)
+    const bool gap_ok    = e.gap <= k.abs_gap_tol + k.rel_gap_tol * e.abs_objective;
+    const bool primal_ok = e.l2_primal_residual <= k.abs_primal_tol + k.rel_primal_tol * k.l2_norm_b;
+    const bool dual_ok   = e.l2_dual_residual <= k.abs_dual_tol + k.rel_dual_tol * k.l2_norm_c;
+    e.status             = (dual_ok && primal_ok && gap_ok) ? 1 : (primal_ok ? 7 : 6);
+    // pdlp_restart_strategy.cu:367-380
+    const double w2 = pw * pw;
+    e.kkt = sqrt(w2 * e.l2_primal_residual * e.l2_primal_residual + e.l2_dual_residual * e.l2_dual_residual / w2 +
+                 e.gap * e.gap);
+    e.pad  = 0;
+    out[v] = e;
+  }
+}
+
+// Averages + in-place unscaling ahead of the evaluation (pdlp.cu:1103-1136,
+// weighted_average_solution.cu:114-142, initial_scaling.cu:456-484).
+// mode 0: avg := current (k_internal <= 1); mode 1: avg := sum / sum_weights (0 when nothing was summed)
+__global__ void __launch_bounds__(EW_THREADS) k_average_and_unscale(const pdhg_ctl_t* __restrict__ ctl,
+                                                                    int mode,
+                                                                    int n,
+                                                                    double* __restrict__ v,
+                                                                    const double* __restrict__ sum_v,
+                                                                    double* __restrict__ avg,
+                                                                    const double* __restrict__ scale)
+{
+  const double sw  = ctl->sum_weights;
+  const bool empty = ctl->its_since_restart == 0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double vj = v[j];
+    const double a  = mode == 0 ? vj : (empty ? 0.0 : sum_v[j] / sw);
+    const double d  = scale[j];
+    avg[j]          = a * d;
+    v[j]            = vj * d;
+  }
+}
+// x /= D with 0 for D == 0 (eltwiseDivideCheckZero; initial_scaling.cu:411-427)
+__global__ void __launch_bounds__(EW_THREADS) k_scale_back(int n, double* __restrict__ v, const double* __restrict__ scale)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double d = scale[j];
+    v[j]           = d == 0.0 ? 0.0 : v[j] / d;
+  }
+}
+
+// Squared distance of the restart candidate to the last restart point for primal and dual, then the
+// primal-weight update (pdlp_restart_strategy.cu:685-732, 753-801, 1681-1714).  Single CTA is enough
+// off the hot path?  No: n can be 10M, so grid-wide with an elected finisher.
+__global__ void __launch_bounds__(EW_THREADS) k_restart_distance_and_weight(pdhg_ctl_t* __restrict__ ctl,
+                                                                            int n,
+                                                                            const double* __restrict__ cand_x,
+                                                                            const double* __restrict__ last_x,
+                                                                            int m,
+                                                                            const double* __restrict__ cand_y,
+                                                                            const double* __restrict__ last_y,
+                                                                            double smoothing,
+                                                                            double* __restrict__ parts)
+{
+  __shared__ double red[32];
+  double acc[2]    = {0.0, 0.0};
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double d = last_x[j] - cand_x[j];
+    acc[0] += d * d;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const double d = last_y[i] - cand_y[i];
+    acc[1] += d * d;
+  }
+  if (!publish_and_elect<2>(acc, parts, &ctl->ticket[2], red)) return;
+  const double dp2 = gather_partials(parts, gridDim.x, red);
+  const double dd2 = gather_partials(parts + gridDim.x, gridDim.x, red);
+  if (threadIdx.x != 0) return;
+  const double pd = sqrt(dp2), dd = sqrt(dd2);
+  const double guard = 1.0e-10;
+  if (pd < guard || pd >= 1.0 / guard || dd < guard || dd >= 1.0 / guard) return;
+  const double lw    = smoothing * log(dd / pd) + (1.0 - smoothing) * log(ctl->primal_weight);
+  const double pw    = exp(lw);
+  ctl->primal_weight = pw;
+  ctl->tau           = ctl->step_size / pw;
+  ctl->sigma         = ctl->step_size * pw;
+}
+__global__ void k_reset_after_restart(pdhg_ctl_t* ctl)
+{
+  ctl->sum_weights       = 0.0;
+  ctl->its_since_restart = 0;
+  ctl->pending_avg       = 0;
+}
+
+// =============================================================================================
+// One-time setup kernels: diagonal scaling (initial_scaling.cu:95-408).  Warp per row; not hot.
+// =============================================================================================
+// mode 0: out[row] = max |(a * rs[row]) * cs[col]|        (Ruiz, :95-122)
+// mode 1: out[row] = sum |(a * rs[row]) * cs[col]|^power  (Pock-Chambolle, :177-252)
+// For A^T pass row_scale = variable scaling, col_scale = constraint scaling and `swap_assoc` keeps the
+// reference's association (a * constraint_scale) * variable_scale.
+__global__ void k_row_scaling_stat(int rows,
+                                   const int* __restrict__ off,
+                                   const int* __restrict__ idx,
+                                   const double* __restrict__ val,
+                                   const double* __restrict__ row_scale,
+                                   const double* __restrict__ col_scale,
+                                   int swap_assoc,
+                                   int mode,
+                                   double power,
+                                   double* __restrict__ out)
+{
+  const int lane = threadIdx.x & 31;
+  const int wpb  = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const double rs = row_scale[r];
+    double acc      = 0.0;
+    for (int p = off[r] + lane; p < off[r + 1]; p += 32) {
+      const double cs = col_scale[idx[p]];
+      const double a  = swap_assoc ? fabs((val[p] * cs) * rs) : fabs((val[p] * rs) * cs);
+      if (mode == 0) acc = fmax(acc, a);
+      else acc += pow(a, power);
+    }
+    acc = mode == 0 ? warp_max(acc) : warp_sum(acc);
+    if (lane == 0) out[r] = acc;
+  }
+}
+// cum[i] = stat[i] > 0 ? cum[i] / sqrt(stat[i]) : cum[i]   (utils.cuh:123-129)
+__global__ void k_apply_scaling_stat(int n, double* __restrict__ cum, const double* __restrict__ stat)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double s = stat[j];
+    if (s > 0.0) cum[j] = cum[j] / sqrt(s);
+  }
+}
+// val[p] = val[p] * row_scale[row] * col_scale[col]   (initial_scaling.cu:310-345; same expression for A and A^T)
+__global__ void k_scale_matrix(int rows,
+                               const int* __restrict__ off,
+                               const int* __restrict__ idx,
+                               double* __restrict__ val,
+                               const double* __restrict__ row_scale,
+                               const double* __restrict__ col_scale)
+{
+  const int lane = threadIdx.x & 31;
+  const int wpb  = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const double rs = row_scale[r];
+    for (int p = off[r] + lane; p < off[r + 1]; p += 32) val[p] = val[p] * rs * col_scale[idx[p]];
+  }
+}
+// op 0: v *= s ; op 1: v = s == 0 ? 0 : v / s
+__global__ void k_scale_vector(int n, double* __restrict__ v, const double* __restrict__ s, int op)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double d = s[j];
+    v[j]           = op == 0 ? v[j] * d : (d == 0.0 ? 0.0 : v[j] / d);
+  }
+}
+__global__ void k_fill(int n, double* __restrict__ v, double value)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) v[j] = value;
+}
+__global__ void k_clamp(int n, double* __restrict__ v, const double* __restrict__ lo, const double* __restrict__ hi)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) v[j] = fmin(fmax(v[j], lo[j]), hi[j]);
+}
+
+// Generic deterministic reductions for the setup phase.  kind 0: max |v| ; 1: sum v^2 * w ;
+// 2: sum combine_finite_abs_bounds(lo, hi)^2 * w (utils.cuh:140-148).  Single-CTA finish via ticket.
+__global__ void __launch_bounds__(EW_THREADS) k_setup_reduce(int kind,
+                                                             int n,
+                                                             const double* __restrict__ a,
+                                                             const double* __restrict__ b,
+                                                             double weight,
+                                                             double* __restrict__ parts,
+                                                             unsigned* __restrict__ ticket,
+                                                             double* __restrict__ out)
+{
+  __shared__ double red[32];
+  __shared__ bool is_last;
+  double acc       = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    if (kind == 0) {
+      acc = fmax(acc, fabs(a[j]));
+    } else if (kind == 1) {
+      acc += a[j] * a[j] * weight;
+    } else {
+      double v = 0.0;
+      if (isfinite(b[j])) v = fmax(v, fabs(b[j]));
+      if (isfinite(a[j])) v = fmax(v, fabs(a[j]));
+      acc += v * v * weight;
+    }
+  }
+  const double t = kind == 0 ? block_reduce<true>(acc, red) : block_reduce<false>(acc, red);
+  if (threadIdx.x == 0) {
+    parts[blockIdx.x] = t;
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double s = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s = kind == 0 ? fmax(s, __ldcg(parts + i)) : s + __ldcg(parts + i);
+  s = kind == 0 ? block_reduce<true>(s, red) : block_reduce<false>(s, red);
+  if (threadIdx.x == 0) *out = s;
+}
+
+}  // namespace cuopt_b200

@@ -1,0 +1,840 @@
+// B200-native PDLP driver: device data layout, setup (transpose, diagonal scaling), the
+// batched PDHG loop and the major-iteration logic (termination test + KKT restart).
+//
+// Control flow follows pdlp_solver_t::run_solver (cpp/src/linear_programming/pdlp.cu:984-1185)
+// with these structural differences:
+//   * the reference synchronises the host once per PDHG iteration to read the accept/reject flag
+//     (adaptive_step_size_strategy.cu:228); here a whole batch of attempts (up to the next major
+//     iteration) is enqueued as one CUDA graph and the device decides accept/reject itself;
+//   * per major iteration the reference issues ~40 library calls and two device->host syncs; here it is
+//     two element-wise launches, two fused SpMV launches evaluating the current AND the average iterate
+//     in a single pass over A and A^T, and one sync.
+// HBM layout (all fp64 / int32, one cudaMalloc each): A and A^T as CSR (scaled, hot) + their unscaled
+// copies (termination only) + int4 row-block descriptors; 2x(x, y, A^T y) ping-pong buffers; xbar;
+// running sums; averages; last-restart point; reduced costs; bound / cost vectors (scaled + unscaled).
+#include "pdlp_solver.hpp"
+
+#include "pdlp_kernels.cuh"
+
+#include <math_constants.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <map>
+#include <string>
+
+namespace cuopt_b200 {
+
+namespace {
+
+struct csr_dev_t {
+  int rows = 0, cols = 0, nnz = 0, n_blocks = 0;
+  dvec<int> off, idx;
+  dvec<double> val;
+  dvec<int4> blk;
+  const csr_dev_t* structure = nullptr;  // scaled copies share offsets / indices / row blocks with the original
+  const int* off_ptr() const { return structure ? structure->off.data() : off.data(); }
+  const int* idx_ptr() const { return structure ? structure->idx.data() : idx.data(); }
+  const int4* blk_ptr() const { return structure ? structure->blk.data() : blk.data(); }
+  csr_view_t view() const { return csr_view_t{rows, off_ptr(), idx_ptr(), val.data(), n_blocks, blk_ptr()}; }
+  // same sparsity pattern, own values (device-to-device copy)
+  void alias_structure_copy_values(const csr_dev_t& o, cudaStream_t s)
+  {
+    rows = o.rows; cols = o.cols; nnz = o.nnz; n_blocks = o.n_blocks;
+    structure = &o;
+    val.copy_from(o.val, s);
+  }
+};
+
+// Cut consecutive rows into blocks of <= SPMV_NNZ nonzeros and <= SPMV_ROWS rows; a longer row is a block of its own.
+std::vector<int4> build_row_blocks(const std::vector<int>& off)
+{
+  std::vector<int4> blocks;
+  const int rows = (int)off.size() - 1;
+  int r          = 0;
+  while (r < rows) {
+    const int lo = off[r];
+    int r1       = r;
+    if (off[r + 1] - lo > SPMV_NNZ) {
+      r1 = r + 1;
+    } else {
+      while (r1 < rows && off[r1 + 1] - lo <= SPMV_NNZ && (r1 - r) < SPMV_ROWS) ++r1;
+    }
+    blocks.push_back(make_int4(r, r1, lo, off[r1]));
+    r = r1;
+  }
+  return blocks;
+}
+
+void upload_csr(csr_dev_t& d, int rows, int cols, const std::vector<int>& off, const std::vector<int>& idx,
+                const std::vector<double>& val, cudaStream_t s)
+{
+  d.rows = rows;
+  d.cols = cols;
+  d.nnz  = (int)val.size();
+  d.off.upload(off, s);
+  d.idx.upload(idx, s);
+  d.val.upload(val, s);
+  auto blocks = build_row_blocks(off);
+  d.n_blocks  = (int)blocks.size();
+  d.blk.upload(blocks, s);
+}
+
+// Stable CSR transpose on the host (row indices ascending inside each transposed row — the order
+// cusparseCsr2cscEx2 gives the reference, mip/problem/problem.cu:277-309).
+void transpose_host(int rows, int cols, const std::vector<int>& off, const std::vector<int>& idx,
+                    const std::vector<double>& val, std::vector<int>& toff, std::vector<int>& tidx,
+                    std::vector<double>& tval)
+{
+  toff.assign(cols + 1, 0);
+  tidx.resize(idx.size());
+  tval.resize(val.size());
+  for (int j : idx) toff[j + 1]++;
+  for (int j = 0; j < cols; ++j) toff[j + 1] += toff[j];
+  std::vector<int> cur(toff.begin(), toff.end() - 1);
+  for (int i = 0; i < rows; ++i)
+    for (int p = off[i]; p < off[i + 1]; ++p) {
+      const int q = cur[idx[p]]++;
+      tidx[q]     = i;
+      tval[q]     = val[p];
+    }
+}
+
+int ew_grid(int n, int sms) { return std::max(1, std::min((n + EW_THREADS - 1) / EW_THREADS, sms * 8)); }
+
+double now_seconds()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct pdlp_solver_t::impl_t {
+  // ---- problem ----
+  int m = 0, n = 0, nnz = 0;
+  bool maximize    = false;
+  double obj_scale = 1.0, obj_offset = 0.0;
+  pdlp_hyper_params_t hp;
+  pdlp_settings_t st;
+  cudaStream_t stream = nullptr;
+  int sms             = 148;
+
+  csr_dev_t A, AT, As, ATs;
+  dvec<double> c, l, u, lc, uc, cs, ls, us, lcs, ucs, Dr, Dc;
+  dvec<double> xbuf[2], ybuf[2], atybuf[2], xbar, sum_x, sum_y, x_avg, y_avg, x_lr, y_lr, rc_cur, rc_avg;
+  dvec<double> part_dy2, part_k3, part_rows, part_cols, part_misc, scratch_n, scratch_m, d_scalar;
+  dvec<unsigned> d_ticket;
+  dvec<pdhg_ctl_t> d_ctl;
+  dvec<eval_t> d_eval;
+  pdhg_ctl_t* h_ctl = nullptr;  // pinned mirrors
+  eval_t* h_eval    = nullptr;
+  double* h_scalar  = nullptr;
+  int grid_k1 = 1, grid_k2 = 1, grid_k3 = 1, grid_er = 1, grid_ec = 1, grid_n = 1, grid_m = 1, grid_misc = 1;
+  std::map<int, cudaGraphExec_t> graphs;
+  bool use_graphs = true;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+
+  // ---- host-side loop state (names follow pdlp.cu / pdlp_restart_strategy.cu) ----
+  int total_pdlp_iterations      = 0;
+  bool initialised               = false;
+  bool need_aty                  = true;   // first step, or first step after a restart to the average
+  bool last_restart_was_average  = false;
+  double last_candidate_kkt      = 0.0, last_restart_kkt = 0.0;
+  double l2_norm_b = 0.0, l2_norm_c = 0.0;
+  lp_solution_t sol;
+  bool finished   = false;
+  double t_start  = 0.0;
+  long long launches = 0;
+
+  ~impl_t()
+  {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    if (ev_a) cudaEventDestroy(ev_a);
+    if (ev_b) cudaEventDestroy(ev_b);
+    if (h_ctl) cudaFreeHost(h_ctl);
+    if (h_eval) cudaFreeHost(h_eval);
+    if (h_scalar) cudaFreeHost(h_scalar);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  void sync() { CUOPT_CUDA_TRY(cudaStreamSynchronize(stream)); }
+  void check_launch() { CUOPT_CUDA_TRY(cudaGetLastError()); }
+
+  // ------------------------------------------------------------------------------- construction
+  void build(const lp_problem_t& p, const pdlp_settings_t& settings)
+  {
+    p.check_representation();
+    st       = settings;
+    hp       = pdlp_hyper_params_t::preset(settings.pdlp_solver_mode);
+    m        = p.n_constraints;
+    n        = p.n_variables;
+    nnz      = p.nnz();
+    maximize = p.maximize;
+    if (m == 0 || nnz == 0) {
+      // solve.cu:355-360: PDLP cannot run without constraints -> NumericalError solution
+      throw lp_error(error_type_t::Success, "No constraints in the problem: PDLP can't be run");
+    }
+    int dev = 0;
+    CUOPT_CUDA_TRY(cudaGetDevice(&dev));
+    CUOPT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CUOPT_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUOPT_CUDA_TRY(cudaEventCreate(&ev_a));
+    CUOPT_CUDA_TRY(cudaEventCreate(&ev_b));
+    CUOPT_CUDA_TRY(cudaMallocHost(&h_ctl, sizeof(pdhg_ctl_t)));
+    CUOPT_CUDA_TRY(cudaMallocHost(&h_eval, 2 * sizeof(eval_t)));
+    CUOPT_CUDA_TRY(cudaMallocHost(&h_scalar, 8 * sizeof(double)));
+    if (const char* e = std::getenv("CUOPT_B200_NO_GRAPH")) use_graphs = !(e[0] == '1');
+
+    // problem_t construction semantics (mip/problem/problem.cu:55-93, problem_helpers.cuh:34-142)
+    std::vector<double> hc = p.objective_coefficients, hl, hu, hlc, huc;
+    p.variable_bounds(hl, hu);
+    p.row_bounds(hlc, huc);
+    obj_scale  = p.objective_scaling_factor;
+    obj_offset = p.objective_offset;
+    if (maximize) {
+      for (auto& v : hc) v = -v;
+      obj_scale = -obj_scale;
+    }
+    for (int j = 0; j < n; ++j)
+      if (hl[j] > hu[j]) throw lp_error(error_type_t::ValidationError, "Variable lower bound above upper bound");
+    for (int i = 0; i < m; ++i)
+      if (hlc[i] > huc[i]) throw lp_error(error_type_t::ValidationError, "Constraint lower bound above upper bound");
+
+    std::vector<int> toff, tidx;
+    std::vector<double> tval;
+    transpose_host(m, n, p.A_offsets, p.A_indices, p.A_values, toff, tidx, tval);
+    upload_csr(A, m, n, p.A_offsets, p.A_indices, p.A_values, stream);
+    upload_csr(AT, n, m, toff, tidx, tval, stream);
+    As.alias_structure_copy_values(A, stream);
+    ATs.alias_structure_copy_values(AT, stream);
+    c.upload(hc, stream); l.upload(hl, stream); u.upload(hu, stream); lc.upload(hlc, stream); uc.upload(huc, stream);
+    cs.copy_from(c, stream); ls.copy_from(l, stream); us.copy_from(u, stream); lcs.copy_from(lc, stream); ucs.copy_from(uc, stream);
+
+    for (int b = 0; b < 2; ++b) {
+      xbuf[b].resize(n); xbuf[b].zero(stream);
+      ybuf[b].resize(m); ybuf[b].zero(stream);
+      atybuf[b].resize(n); atybuf[b].zero(stream);
+    }
+    for (dvec<double>* v : {&xbar, &sum_x, &x_avg, &x_lr, &rc_cur, &rc_avg, &scratch_n}) { v->resize(n); v->zero(stream); }
+    for (dvec<double>* v : {&sum_y, &y_avg, &y_lr, &scratch_m}) { v->resize(m); v->zero(stream); }
+    Dr.resize(m);
+    Dc.resize(n);
+
+    // persistent grids: one wave of resident CTAs
+    auto occ_grid = [&](const void* kernel, int blocks) {
+      int per_sm = 1;
+      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPMV_THREADS, 0));
+      return std::max(1, std::min(blocks, sms * std::max(per_sm, 1)));
+    };
+    grid_k2   = occ_grid((const void*)k_dual_step, As.n_blocks);
+    grid_k3   = occ_grid((const void*)k_transpose_step, ATs.n_blocks);
+    grid_er   = occ_grid((const void*)k_eval_rows, A.n_blocks);
+    grid_ec   = occ_grid((const void*)k_eval_cols, AT.n_blocks);
+    grid_n    = ew_grid(n, sms);
+    grid_m    = ew_grid(m, sms);
+    grid_k1   = grid_n;
+    grid_misc = ew_grid(std::max(n, m), sms);
+    part_dy2.resize(grid_k2);
+    part_k3.resize(2 * (size_t)grid_k3);
+    part_rows.resize(6 * (size_t)grid_er);
+    part_cols.resize(8 * (size_t)grid_ec);
+    part_misc.resize(2 * (size_t)std::max(grid_misc, ew_grid(nnz, sms)));
+    d_scalar.resize(8);
+    d_ticket.resize(4);
+    d_ticket.zero(stream);
+    d_ctl.resize(1);
+    d_ctl.zero(stream);
+    d_eval.resize(2);
+    d_eval.zero(stream);
+    sync();
+  }
+
+  // deterministic setup reduction, result on the host
+  double setup_reduce(int kind, int count, const double* a, const double* b, double weight)
+  {
+    const int g = ew_grid(count, sms);
+    k_setup_reduce<<<g, EW_THREADS, 0, stream>>>(kind, count, a, b, weight, part_misc.data(), d_ticket.data(), d_scalar.data());
+    check_launch();
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(h_scalar, d_scalar.data(), sizeof(double), cudaMemcpyDeviceToHost, stream));
+    sync();
+    return h_scalar[0];
+  }
+
+  // initial_scaling.cu:85-307
+  void compute_scaling_vectors()
+  {
+    k_fill<<<grid_m, EW_THREADS, 0, stream>>>(m, Dr.data(), 1.0);
+    k_fill<<<grid_n, EW_THREADS, 0, stream>>>(n, Dc.data(), 1.0);
+    const int wg_m = std::max(1, std::min((m + 7) / 8, sms * 16));
+    const int wg_n = std::max(1, std::min((n + 7) / 8, sms * 16));
+    auto pass      = [&](int mode, double pr, double pc) {
+      // statistics of rows of A and of rows of A^T (columns of A), both with the OLD scaling vectors
+      k_row_scaling_stat<<<wg_m, 256, 0, stream>>>(m, A.off.data(), A.idx.data(), A.val.data(), Dr.data(), Dc.data(), 0,
+                                                   mode, pr, scratch_m.data());
+      k_row_scaling_stat<<<wg_n, 256, 0, stream>>>(n, AT.off.data(), AT.idx.data(), AT.val.data(), Dc.data(), Dr.data(),
+                                                   1, mode, pc, scratch_n.data());
+      k_apply_scaling_stat<<<grid_m, EW_THREADS, 0, stream>>>(m, Dr.data(), scratch_m.data());
+      k_apply_scaling_stat<<<grid_n, EW_THREADS, 0, stream>>>(n, Dc.data(), scratch_n.data());
+    };
+    if (hp.do_ruiz_scaling)
+      for (int it = 0; it < hp.default_l_inf_ruiz_iterations; ++it) pass(0, 0.0, 0.0);
+    if (hp.do_pock_chambolle_scaling) {
+      const double alpha = hp.default_alpha_pock_chambolle_rescaling;
+      if (!(alpha >= 0.0 && alpha <= 2.0)) throw lp_error(error_type_t::ValidationError, "Invalid Pock-Chambolle alpha");
+      pass(1, alpha, 2.0 - alpha);
+    }
+    check_launch();
+  }
+
+  // initial_scaling.cu:348-408
+  void scale_problem()
+  {
+    const int wg_m = std::max(1, std::min((m + 7) / 8, sms * 16));
+    const int wg_n = std::max(1, std::min((n + 7) / 8, sms * 16));
+    k_scale_matrix<<<wg_m, 256, 0, stream>>>(m, As.off_ptr(), As.idx_ptr(), As.val.data(), Dr.data(), Dc.data());
+    k_scale_matrix<<<wg_n, 256, 0, stream>>>(n, ATs.off_ptr(), ATs.idx_ptr(), ATs.val.data(), Dc.data(), Dr.data());
+    k_scale_vector<<<grid_n, EW_THREADS, 0, stream>>>(n, cs.data(), Dc.data(), 0);
+    k_scale_vector<<<grid_n, EW_THREADS, 0, stream>>>(n, ls.data(), Dc.data(), 1);
+    k_scale_vector<<<grid_n, EW_THREADS, 0, stream>>>(n, us.data(), Dc.data(), 1);
+    k_scale_vector<<<grid_m, EW_THREADS, 0, stream>>>(m, lcs.data(), Dr.data(), 0);
+    k_scale_vector<<<grid_m, EW_THREADS, 0, stream>>>(m, ucs.data(), Dr.data(), 0);
+    check_launch();
+    // x = y = 0 at this point: scaling the (zero) iterates is a no-op
+  }
+
+  double initial_step_size(const csr_dev_t& M)  // pdlp.cu:1225-1258
+  {
+    const double mx = setup_reduce(0, M.nnz, M.val.data(), nullptr, 0.0);
+    return mx == 0.0 ? 0.0 : hp.initial_step_size_scaling / mx;
+  }
+  double initial_primal_weight(const dvec<double>& cc, const dvec<double>& lo, const dvec<double>& hi)  // pdlp.cu:1261-1309
+  {
+    const double bn = std::sqrt(setup_reduce(2, m, lo.data(), hi.data(), hp.initial_primal_weight_b_scaling));
+    const double cn = std::sqrt(setup_reduce(1, n, cc.data(), nullptr, hp.initial_primal_weight_c_scaling));
+    return (bn > 0.0 && cn > 0.0) ? hp.primal_importance * (cn / bn) : hp.primal_importance;
+  }
+
+  void initialise()
+  {
+    if (initialised) return;
+    const double t0 = now_seconds();
+    // norms of the unscaled problem used by the relative tolerances (convergence_information.cu:74-82)
+    l2_norm_c = std::sqrt(setup_reduce(1, n, c.data(), nullptr, 1.0));
+    l2_norm_b = std::sqrt(setup_reduce(2, m, lc.data(), uc.data(), 1.0));
+    compute_scaling_vectors();
+    double step = 0.0, weight = 0.0;
+    if (hp.compute_initial_step_size_before_scaling) step = initial_step_size(A);
+    if (hp.compute_initial_primal_weight_before_scaling) weight = initial_primal_weight(c, lc, uc);
+    scale_problem();
+    if (!hp.compute_initial_step_size_before_scaling) step = initial_step_size(As);
+    if (!hp.compute_initial_primal_weight_before_scaling) weight = initial_primal_weight(cs, lcs, ucs);
+
+    pdhg_ctl_t k{};
+    k.step_size          = step;
+    k.primal_weight      = weight;
+    k.tau                = step / weight;  // adaptive_step_size_strategy.cu:348-366
+    k.sigma              = step * weight;
+    k.reduction_exponent = hp.reduction_exponent;
+    k.growth_exponent    = hp.growth_exponent;
+    k.primal_smoothing   = hp.primal_distance_smoothing;
+    k.dual_smoothing     = hp.dual_distance_smoothing;
+    *h_ctl               = k;
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(d_ctl.data(), h_ctl, sizeof(k), cudaMemcpyHostToDevice, stream));
+    if (hp.project_initial_primal) {  // pdlp.cu:1041-1056
+      k_clamp<<<grid_n, EW_THREADS, 0, stream>>>(n, xbuf[0].data(), ls.data(), us.data());
+      k_clamp<<<grid_n, EW_THREADS, 0, stream>>>(n, x_avg.data(), ls.data(), us.data());
+    }
+    check_launch();
+    sync();
+    sol.stats.initial_step_size     = step;
+    sol.stats.initial_primal_weight = weight;
+    sol.stats.setup_seconds += now_seconds() - t0;
+    initialised = true;
+  }
+
+  // ------------------------------------------------------------------------------ PDHG batches
+  void enqueue_attempt()
+  {
+    k_primal_step<<<grid_k1, EW_THREADS, 0, stream>>>(d_ctl.data(), n, xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
+                                                      atybuf[1].data(), cs.data(), ls.data(), us.data(), sum_x.data(),
+                                                      xbar.data());
+    k_dual_step<<<grid_k2, SPMV_THREADS, 0, stream>>>(d_ctl.data(), As.view(), xbar.data(), ybuf[0].data(), ybuf[1].data(),
+                                                      lcs.data(), ucs.data(), sum_y.data(), part_dy2.data());
+    k_transpose_step<<<grid_k3, SPMV_THREADS, 0, stream>>>(d_ctl.data(), ATs.view(), ybuf[0].data(), ybuf[1].data(),
+                                                           xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
+                                                           atybuf[1].data(), part_k3.data(), part_dy2.data(), grid_k2);
+  }
+
+  void launch_attempts(int count)
+  {
+    if (count <= 0) return;
+    launches += 3LL * count;
+    if (!use_graphs || count == 1) {
+      for (int i = 0; i < count; ++i) enqueue_attempt();
+      check_launch();
+      return;
+    }
+    auto it = graphs.find(count);
+    if (it == graphs.end()) {
+      cudaGraph_t g;
+      CUOPT_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      for (int i = 0; i < count; ++i) enqueue_attempt();
+      CUOPT_CUDA_TRY(cudaStreamEndCapture(stream, &g));
+      cudaGraphExec_t ge;
+      CUOPT_CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      it = graphs.emplace(count, ge).first;
+    }
+    CUOPT_CUDA_TRY(cudaGraphLaunch(it->second, stream));
+  }
+
+  void fetch_ctl()
+  {
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(h_ctl, d_ctl.data(), sizeof(pdhg_ctl_t), cudaMemcpyDeviceToHost, stream));
+    sync();
+  }
+
+  // take_step x `steps` (pdlp.cu:1188-1222): returns when `steps` more steps were accepted or an error was flagged.
+  void run_steps(int steps)
+  {
+    if (steps <= 0) return;
+    CUOPT_CUDA_TRY(cudaEventRecord(ev_a, stream));
+    if (need_aty) {  // pdhg.cu:183-202
+      const int cur = h_ctl->parity;
+      k_spmv<<<grid_k3, SPMV_THREADS, 0, stream>>>(ATs.view(), ybuf[cur].data(), atybuf[cur].data());
+      ++launches;
+      need_aty = false;
+    }
+    k_begin_batch<<<1, 1, 0, stream>>>(d_ctl.data(), steps);
+    const int target = h_ctl->accepted + steps;
+    int todo         = steps;
+    while (true) {
+      // a couple of spare attempts cover the occasional rejected step without another round trip
+      launch_attempts(todo + (todo >= 16 ? 2 : 0));
+      k_flush_average<<<grid_misc, EW_THREADS, 0, stream>>>(d_ctl.data(), n, xbuf[0].data(), xbuf[1].data(), sum_x.data(),
+                                                            m, ybuf[0].data(), ybuf[1].data(), sum_y.data());
+      k_clear_pending<<<1, 1, 0, stream>>>(d_ctl.data());
+      launches += 3;
+      check_launch();
+      fetch_ctl();
+      if (h_ctl->valid == -1 || h_ctl->accepted >= target) break;
+      todo = target - h_ctl->accepted;
+    }
+    CUOPT_CUDA_TRY(cudaEventRecord(ev_b, stream));
+    CUOPT_CUDA_TRY(cudaEventSynchronize(ev_b));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev_a, ev_b);
+    sol.stats.pdhg_loop_seconds += ms * 1e-3;
+  }
+
+  // ------------------------------------------------------------------------- major iteration
+  eval_consts_t eval_consts() const
+  {
+    eval_consts_t k;
+    k.objective_scaling_factor = obj_scale;
+    k.objective_offset         = obj_offset;
+    k.abs_gap_tol              = st.absolute_gap_tolerance;
+    k.rel_gap_tol              = st.relative_gap_tolerance;
+    k.abs_primal_tol           = st.absolute_primal_tolerance;
+    k.rel_primal_tol           = st.relative_primal_tolerance;
+    k.abs_dual_tol             = st.absolute_dual_tolerance;
+    k.rel_dual_tol             = st.relative_dual_tolerance;
+    k.l2_norm_b                = l2_norm_b;
+    k.l2_norm_c                = l2_norm_c;
+    k.reduced_cost_rule        = hp.handle_some_primal_gradients_on_finite_bounds_as_residuals ? 1 : 0;
+    return k;
+  }
+
+  // averages, in-place unscaling, evaluation of current and average (pdlp.cu:1103-1142 up to check_termination's inputs)
+  void evaluate_iterates()
+  {
+    const int cur  = h_ctl->parity;
+    const int mode = (h_ctl->accepted <= 1) ? 0 : 1;
+    k_average_and_unscale<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), mode, n, xbuf[cur].data(), sum_x.data(),
+                                                             x_avg.data(), Dc.data());
+    k_average_and_unscale<<<grid_m, EW_THREADS, 0, stream>>>(d_ctl.data(), mode, m, ybuf[cur].data(), sum_y.data(),
+                                                             y_avg.data(), Dr.data());
+    k_eval_rows<<<grid_er, SPMV_THREADS, 0, stream>>>(A.view(), xbuf[cur].data(), x_avg.data(), ybuf[cur].data(),
+                                                      y_avg.data(), lc.data(), uc.data(), part_rows.data());
+    k_eval_cols<<<grid_ec, SPMV_THREADS, 0, stream>>>(d_ctl.data(), AT.view(), xbuf[cur].data(), x_avg.data(),
+                                                      ybuf[cur].data(), y_avg.data(), c.data(), l.data(), u.data(),
+                                                      rc_cur.data(), rc_avg.data(), part_cols.data(), part_rows.data(),
+                                                      grid_er, eval_consts(), d_eval.data());
+    launches += 4;
+    check_launch();
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(h_eval, d_eval.data(), 2 * sizeof(eval_t), cudaMemcpyDeviceToHost, stream));
+    sync();
+  }
+
+  void fill_solution(bool average, termination_status_t status)  // termination_strategy.cu:270-357
+  {
+    const int cur   = h_ctl->parity;
+    const eval_t& e = h_eval[average ? 1 : 0];
+    sol.primal.resize(n);
+    sol.dual.resize(m);
+    sol.reduced_cost.resize(n);
+    (average ? x_avg : xbuf[cur]).download(sol.primal.data(), stream);
+    (average ? y_avg : ybuf[cur]).download(sol.dual.data(), stream);
+    (average ? rc_avg : rc_cur).download(sol.reduced_cost.data(), stream);
+    fetch_ctl();
+    sol.termination_status                    = status;
+    sol.error_status                          = 0;
+    lp_stats_t& s                             = sol.stats;
+    s.number_of_steps_taken                   = h_ctl->accepted;
+    s.total_number_of_attempted_steps         = h_ctl->attempts;
+    s.l2_primal_residual                      = e.l2_primal_residual;
+    s.l2_dual_residual                        = e.l2_dual_residual;
+    s.l2_relative_primal_residual             = e.l2_primal_residual / (1.0 + l2_norm_b);
+    s.l2_relative_dual_residual               = e.l2_dual_residual / (1.0 + l2_norm_c);
+    s.primal_objective                        = e.primal_objective;
+    s.dual_objective                          = e.dual_objective;
+    s.gap                                     = e.gap;
+    s.relative_gap                            = e.gap / (1.0 + std::fabs(e.primal_objective) + std::fabs(e.dual_objective));
+    s.solved_by_pdlp                          = 1;
+    s.final_step_size                         = h_ctl->step_size;
+    s.final_primal_weight                     = h_ctl->primal_weight;
+    s.kernel_launches                         = launches;
+    finished                                  = true;
+  }
+
+  bool check_limits()  // pdlp.cu:265-331
+  {
+    if (now_seconds() - t_start >= st.time_limit) {
+      fill_solution(false, termination_status_t::TimeLimit);
+      return true;
+    }
+    if (h_ctl->accepted >= st.iteration_limit) {
+      fill_solution(false, termination_status_t::IterationLimit);
+      return true;
+    }
+    return false;
+  }
+
+  bool check_termination()  // pdlp.cu:538-802 (first_primal_feasible handled, infeasibility detection not implemented)
+  {
+    if (total_pdlp_iterations <= 1) return check_limits();
+    const int sc = h_eval[0].status, sa = h_eval[1].status;
+    if (st.first_primal_feasible) {  // :587-633
+      if (sa == 7 && sc == 7) {
+        fill_solution(!(h_eval[0].l2_primal_residual < h_eval[1].l2_primal_residual), termination_status_t::PrimalFeasible);
+        return true;
+      } else if (sc == 7) {
+        fill_solution(false, termination_status_t::PrimalFeasible);
+        return true;
+      } else if (sa == 7) {
+        fill_solution(true, termination_status_t::PrimalFeasible);
+        return true;
+      }
+    }
+    if (sa == 1 && sc == 1) {
+      fill_solution(!(h_eval[0].kkt < h_eval[1].kkt), termination_status_t::Optimal);
+      return true;
+    }
+    if (sa == 1) { fill_solution(true, termination_status_t::Optimal); return true; }
+    if (sc == 1) { fill_solution(false, termination_status_t::Optimal); return true; }
+    if (h_ctl->valid == -1) {  // :780-789
+      fetch_ctl();
+      sol                                        = lp_solution_t{};
+      sol.termination_status                     = termination_status_t::NumericalError;
+      sol.stats.number_of_steps_taken            = h_ctl->accepted;
+      sol.stats.total_number_of_attempted_steps  = h_ctl->attempts;
+      sol.stats.kernel_launches                  = launches;
+      finished                                   = true;
+      return true;
+    }
+    return check_limits();
+  }
+
+  bool should_do_artificial_restart(int total_iterations) const  // pdlp_restart_strategy.cu:940-961
+  {
+    return h_ctl->its_since_restart >= hp.default_artificial_restart_threshold * total_iterations;
+  }
+
+  void kkt_restart()  // pdlp_restart_strategy.cu:468-641
+  {
+    const int cur        = h_ctl->parity;
+    const double kkt_cur = h_eval[0].kkt;
+    if (h_ctl->its_since_restart == 0) {
+      last_candidate_kkt = kkt_cur;
+      last_restart_kkt   = kkt_cur;
+      return;
+    }
+    const double kkt_avg = h_eval[1].kkt;
+    const bool to_avg    = !(kkt_cur < kkt_avg);
+    const double cand    = to_avg ? kkt_avg : kkt_cur;
+    const bool decay     = cand < hp.sufficient_reduction_for_restart * last_restart_kkt ||
+                       (cand < hp.necessary_reduction_for_restart * last_restart_kkt && cand > last_candidate_kkt);
+    if (should_do_artificial_restart(total_pdlp_iterations) || decay) {
+      const bool use_avg = to_avg && !hp.never_restart_to_average;
+      dvec<double>& cx   = use_avg ? x_avg : xbuf[cur];
+      dvec<double>& cy   = use_avg ? y_avg : ybuf[cur];
+      k_restart_distance_and_weight<<<grid_misc, EW_THREADS, 0, stream>>>(
+        d_ctl.data(), n, cx.data(), x_lr.data(), m, cy.data(), y_lr.data(), hp.primal_weight_update_smoothing,
+        part_misc.data());
+      if (use_avg) {
+        xbuf[cur].copy_from(x_avg, stream);
+        ybuf[cur].copy_from(y_avg, stream);
+        need_aty = true;
+      }
+      last_restart_was_average = use_avg;
+      x_lr.copy_from(cx, stream);
+      y_lr.copy_from(cy, stream);
+      sum_x.zero(stream);
+      sum_y.zero(stream);
+      k_reset_after_restart<<<1, 1, 0, stream>>>(d_ctl.data());
+      launches += 2;
+      check_launch();
+      last_restart_kkt = cand;
+      sol.stats.n_restarts += 1;
+      fetch_ctl();
+    }
+    last_candidate_kkt = cand;
+  }
+
+  // number of PDHG steps until the outer loop has to look at the iterate again
+  int steps_until_next_check() const
+  {
+    const int k = total_pdlp_iterations;
+    int t       = 1;
+    while (true) {
+      const int kk = k + t;
+      if (((kk % hp.major_iteration == 0) && kk > 0) || kk <= hp.min_iteration_restart) break;
+      if (hp.artificial_restart_in_main_loop &&
+          (h_ctl->its_since_restart + t) >= hp.default_artificial_restart_threshold * kk)
+        break;
+      ++t;
+    }
+    return t;
+  }
+
+  // pdlp.cu:1081-1185.  budget < 0: run to termination; otherwise stop after `budget` accepted steps.
+  bool outer_loop(int budget)
+  {
+    initialise();
+    if (finished) return true;
+    if (t_start == 0.0) t_start = now_seconds();
+    while (true) {
+      const int k          = total_pdlp_iterations;
+      const bool is_major  = ((k % hp.major_iteration == 0) && k > 0) || (k <= hp.min_iteration_restart);
+      const bool error     = h_ctl->valid == -1;
+      const bool artificial = hp.artificial_restart_in_main_loop && should_do_artificial_restart(k);
+      if (is_major || artificial || error) {
+        CUOPT_CUDA_TRY(cudaEventRecord(ev_a, stream));
+        sol.stats.n_major_iterations += 1;
+        evaluate_iterates();
+        if (check_termination()) return true;
+        const int cur = h_ctl->parity;
+        if (hp.rescale_for_restart) {  // pdlp.cu:1144-1149
+          k_scale_back<<<grid_n, EW_THREADS, 0, stream>>>(n, x_avg.data(), Dc.data());
+          k_scale_back<<<grid_m, EW_THREADS, 0, stream>>>(m, y_avg.data(), Dr.data());
+          k_scale_back<<<grid_n, EW_THREADS, 0, stream>>>(n, xbuf[cur].data(), Dc.data());
+          k_scale_back<<<grid_m, EW_THREADS, 0, stream>>>(m, ybuf[cur].data(), Dr.data());
+          launches += 4;
+        }
+        if (hp.restart_strategy == 1) kkt_restart();
+        else if (hp.restart_strategy == 2)
+          throw lp_error(error_type_t::ValidationError,
+                         "pdlp_solver_mode Methodical1 (trust-region restart) is not implemented in this build");
+        if (!hp.rescale_for_restart) {  // pdlp.cu:1168-1175
+          k_scale_back<<<grid_n, EW_THREADS, 0, stream>>>(n, xbuf[cur].data(), Dc.data());
+          k_scale_back<<<grid_m, EW_THREADS, 0, stream>>>(m, ybuf[cur].data(), Dr.data());
+          launches += 2;
+        }
+        check_launch();
+        CUOPT_CUDA_TRY(cudaEventRecord(ev_b, stream));
+        CUOPT_CUDA_TRY(cudaEventSynchronize(ev_b));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev_a, ev_b);
+        sol.stats.termination_seconds += ms * 1e-3;
+      }
+      if (budget == 0) return false;
+      int steps = steps_until_next_check();
+      if (budget > 0) steps = std::min(steps, budget);
+      const int before = h_ctl->accepted;
+      run_steps(steps);
+      const int done = h_ctl->accepted - before;
+      total_pdlp_iterations += done;
+      if (budget > 0) budget -= done;
+      if (h_ctl->valid == -1 && done < steps) {
+        // the batch stopped on a numerical error: the reference's loop would now hit `error_occured`
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+pdlp_solver_t::pdlp_solver_t(const lp_problem_t& problem, const pdlp_settings_t& settings, dist_context_t*)
+  : impl_(new impl_t)
+{
+  const double t0 = now_seconds();
+  impl_->build(problem, settings);
+  impl_->sol.stats.setup_seconds += now_seconds() - t0;
+}
+pdlp_solver_t::~pdlp_solver_t() = default;
+
+void pdlp_solver_t::initialise() { impl_->initialise(); }
+bool pdlp_solver_t::advance(int accepted_steps) { return impl_->outer_loop(accepted_steps); }
+const lp_solution_t& pdlp_solver_t::solution() const { return impl_->sol; }
+
+lp_solution_t pdlp_solver_t::run()
+{
+  impl_t& s        = *impl_;
+  const double t0  = now_seconds();
+  s.t_start        = t0;
+  s.outer_loop(-1);
+  s.sol.stats.solve_time = now_seconds() - t0;
+  return s.sol;
+}
+
+double pdlp_solver_t::scalar(const std::string& name)
+{
+  impl_t& s = *impl_;
+  s.fetch_ctl();
+  const pdhg_ctl_t& k = *s.h_ctl;
+  if (name == "step_size") return k.step_size;
+  if (name == "primal_weight") return k.primal_weight;
+  if (name == "tau") return k.tau;
+  if (name == "sigma") return k.sigma;
+  if (name == "sum_w") return k.sum_weights;
+  if (name == "k_total") return s.total_pdlp_iterations;
+  if (name == "k_pdhg") return k.attempts;
+  if (name == "its_since_restart") return k.its_since_restart;
+  if (name == "interaction") return k.interaction;
+  if (name == "norm_dx2") return k.norm_dx2;
+  if (name == "norm_dy2") return k.norm_dy2;
+  if (name == "l2_norm_b") return s.l2_norm_b;
+  if (name == "l2_norm_c") return s.l2_norm_c;
+  if (name == "last_restart_kkt") return s.last_restart_kkt;
+  if (name == "last_candidate_kkt") return s.last_candidate_kkt;
+  if (name == "n_restarts") return s.sol.stats.n_restarts;
+  if (name == "valid") return k.valid;
+  return std::nan("");
+}
+
+std::vector<double> pdlp_solver_t::vector(const std::string& name)
+{
+  impl_t& s = *impl_;
+  s.fetch_ctl();
+  const int cur         = s.h_ctl->parity;
+  const dvec<double>* v = nullptr;
+  if (name == "x") v = &s.xbuf[cur];
+  else if (name == "y") v = &s.ybuf[cur];
+  else if (name == "aty") v = &s.atybuf[cur];
+  else if (name == "x_next") v = &s.xbuf[cur ^ 1];
+  else if (name == "y_next") v = &s.ybuf[cur ^ 1];
+  else if (name == "aty_next") v = &s.atybuf[cur ^ 1];
+  else if (name == "x_bar") v = &s.xbar;
+  else if (name == "sum_x") v = &s.sum_x;
+  else if (name == "sum_y") v = &s.sum_y;
+  else if (name == "x_avg") v = &s.x_avg;
+  else if (name == "y_avg") v = &s.y_avg;
+  else if (name == "row_scaling") v = &s.Dr;
+  else if (name == "col_scaling") v = &s.Dc;
+  else if (name == "scaled_values") v = &s.As.val;
+  else if (name == "scaled_values_t") v = &s.ATs.val;
+  else if (name == "scaled_c") v = &s.cs;
+  else if (name == "scaled_l") v = &s.ls;
+  else if (name == "scaled_u") v = &s.us;
+  else if (name == "scaled_lc") v = &s.lcs;
+  else if (name == "scaled_uc") v = &s.ucs;
+  else if (name == "x_last_restart") v = &s.x_lr;
+  else if (name == "y_last_restart") v = &s.y_lr;
+  if (!v) throw lp_error(error_type_t::InvalidArgument, "unknown vector " + name);
+  std::vector<double> h(v->size());
+  v->download(h.data(), s.stream);
+  s.sync();
+  return h;
+}
+
+kernel_profile_t pdlp_solver_t::profile_kernels(int warmup_steps, int reps)
+{
+  impl_t& s = *impl_;
+  s.initialise();
+  if (warmup_steps > 0) s.outer_loop(warmup_steps);
+  kernel_profile_t out;
+  out.reps = reps;
+  out.grid_primal = s.grid_k1; out.grid_dual = s.grid_k2; out.grid_transpose = s.grid_k3;
+  // SURVEY.md §8(d) per-kernel algorithmic bytes (gathers counted once per vector element)
+  const double n = s.n, m = s.m, nz = s.nnz;
+  out.bytes_primal_step    = 8.0 * (5 * n + 2 * n + 2 * n);                       // x,c,AtY,l,u | x',xbar | sum_x r/w
+  out.bytes_dual_step      = 12.0 * nz + 4.0 * (m + 1) + 8.0 * (n + 3 * m + m + 2 * m);  // A | xbar gather, y,lc,uc | y' | sum_y r/w
+  out.bytes_transpose_step = 12.0 * nz + 4.0 * (n + 1) + 8.0 * (m + n + 3 * n);   // A^T | y' gather | AtY' | x,x',AtY
+  // make every attempt a "typical" one: previous step accepted (running-sum update fused in) and no batch end
+  s.need_aty = false;
+  k_begin_batch<<<1, 1, 0, s.stream>>>(s.d_ctl.data(), 1 << 30);
+  std::vector<cudaEvent_t> ev(4);
+  for (auto& e : ev) cudaEventCreate(&e);
+  double acc[3] = {0, 0, 0};
+  for (int r = 0; r < reps + 3; ++r) {
+    cudaEventRecord(ev[0], s.stream);
+    k_primal_step<<<s.grid_k1, EW_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.n, s.xbuf[0].data(), s.xbuf[1].data(),
+                                                          s.atybuf[0].data(), s.atybuf[1].data(), s.cs.data(), s.ls.data(),
+                                                          s.us.data(), s.sum_x.data(), s.xbar.data());
+    cudaEventRecord(ev[1], s.stream);
+    k_dual_step<<<s.grid_k2, SPMV_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.As.view(), s.xbar.data(), s.ybuf[0].data(),
+                                                          s.ybuf[1].data(), s.lcs.data(), s.ucs.data(), s.sum_y.data(),
+                                                          s.part_dy2.data());
+    cudaEventRecord(ev[2], s.stream);
+    k_transpose_step<<<s.grid_k3, SPMV_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.ATs.view(), s.ybuf[0].data(),
+                                                               s.ybuf[1].data(), s.xbuf[0].data(), s.xbuf[1].data(),
+                                                               s.atybuf[0].data(), s.atybuf[1].data(), s.part_k3.data(),
+                                                               s.part_dy2.data(), s.grid_k2);
+    cudaEventRecord(ev[3], s.stream);
+    cudaEventSynchronize(ev[3]);
+    if (r >= 3) {
+      for (int q = 0; q < 3; ++q) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[q], ev[q + 1]);
+        acc[q] += ms;
+      }
+    }
+  }
+  s.check_launch();
+  out.ms_primal_step    = acc[0] / reps;
+  out.ms_dual_step      = acc[1] / reps;
+  out.ms_transpose_step = acc[2] / reps;
+  // whole attempts back to back (graph when enabled), no events in between
+  cudaEventRecord(ev[0], s.stream);
+  s.launch_attempts(reps);
+  cudaEventRecord(ev[1], s.stream);
+  cudaEventSynchronize(ev[1]);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev[0], ev[1]);
+  out.ms_iteration = ms / reps;
+  for (auto& e : ev) cudaEventDestroy(e);
+  s.sync();
+  return out;
+}
+
+lp_solution_t solve_lp(const lp_problem_t& problem, const pdlp_settings_t& settings)
+{
+  lp_solution_t sol;
+  try {
+    pdlp_solver_t solver(problem, settings);
+    sol = solver.run();
+  } catch (const lp_error& e) {
+    if (e.type == error_type_t::Success) {  // "cannot run" cases the reference answers with a NumericalError solution
+      sol.termination_status = termination_status_t::NumericalError;
+      sol.error_status       = 0;
+      sol.error_message      = e.what();
+      return sol;
+    }
+    sol                    = lp_solution_t{};
+    sol.termination_status = termination_status_t::NoTermination;
+    sol.error_status       = (int)e.type;
+    sol.error_message      = e.what();
+  } catch (const std::bad_alloc&) {
+    sol                    = lp_solution_t{};
+    sol.error_status       = (int)error_type_t::RuntimeError;
+    sol.error_message      = "Memory allocation failed";
+  } catch (const std::exception& e) {
+    sol                    = lp_solution_t{};
+    sol.error_status       = (int)error_type_t::RuntimeError;
+    sol.error_message      = e.what();
+  }
+  return sol;
+}
+
+}  // namespace cuopt_b200

@@ -1,0 +1,101 @@
+/*
+ * Extension entry points of the B200-native libcuopt LP build.
+ *
+ * The reference C ABI (cuopt_c.h) has no way to read the iteration count, the dual objective or the
+ * residuals of an LP solve: they live in additional_termination_information_t
+ * (cpp/include/cuopt/linear_programming/pdlp/solver_solution.hpp:47-87), reachable from C++ / Python only.
+ * These clearly-prefixed additions expose them, plus a white-box "solver session" used by the parity
+ * tests and by bench.py (device-resident timing, per-kernel roofline) and the multi-GPU bootstrap.
+ * Nothing here changes the behaviour of the 41 reference symbols.
+ */
+#ifndef CUOPT_B200_EXT_H
+#define CUOPT_B200_EXT_H
+
+#include <cuopt/linear_programming/cuopt_c.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* additional_termination_information_t (solver_solution.hpp:47-87) + timing of this build */
+typedef struct cuOptB200LPStats {
+  cuopt_int_t number_of_steps_taken;           /* accepted PDLP iterations */
+  cuopt_int_t total_number_of_attempted_steps; /* PDHG attempts incl. rejected step sizes */
+  cuopt_float_t l2_primal_residual;
+  cuopt_float_t l2_relative_primal_residual;
+  cuopt_float_t l2_dual_residual;
+  cuopt_float_t l2_relative_dual_residual;
+  cuopt_float_t primal_objective;
+  cuopt_float_t dual_objective;
+  cuopt_float_t gap;
+  cuopt_float_t relative_gap;
+  cuopt_int_t solved_by_pdlp;
+  cuopt_int_t n_major_iterations; /* termination / restart evaluations */
+  cuopt_int_t n_restarts;
+  cuopt_int_t reserved;
+  cuopt_float_t solve_time;          /* seconds, wall clock of the solver loop (reference semantics) */
+  cuopt_float_t setup_seconds;       /* host->device upload, transpose, diagonal scaling */
+  cuopt_float_t pdhg_loop_seconds;   /* device time (CUDA events) spent in PDHG batches */
+  cuopt_float_t termination_seconds; /* device time spent in termination / restart passes */
+  cuopt_float_t initial_step_size;
+  cuopt_float_t initial_primal_weight;
+  cuopt_float_t final_step_size;
+  cuopt_float_t final_primal_weight;
+  int64_t kernel_launches; /* kernels of this library launched by the solve */
+} cuOptB200LPStats;
+
+/* Statistics of an LP solution returned by cuOptSolve. */
+cuopt_int_t cuOptB200GetLPStats(cuOptSolution solution, cuOptB200LPStats* stats);
+
+/* ---- solver session: the same solver cuOptSolve runs, driven step by step -------------------- */
+typedef void* cuOptB200Solver;
+
+typedef struct cuOptB200KernelProfile {
+  cuopt_float_t ms_primal_step, ms_dual_step, ms_transpose_step; /* mean device time per launch */
+  cuopt_float_t bytes_primal_step, bytes_dual_step, bytes_transpose_step; /* algorithmic bytes per launch */
+  cuopt_float_t ms_iteration; /* mean per attempt, all three kernels back to back */
+  cuopt_int_t reps;
+  cuopt_int_t grid_primal, grid_dual, grid_transpose;
+} cuOptB200KernelProfile;
+
+/* Upload the problem to the current CUDA device (A, A^T, row-block schedules). */
+cuopt_int_t cuOptB200SolverCreate(cuOptOptimizationProblem problem,
+                                  cuOptSolverSettings settings,
+                                  cuOptB200Solver* solver_ptr);
+void cuOptB200SolverDestroy(cuOptB200Solver* solver_ptr);
+/* Diagonal scaling + initial step size / primal weight (what cuOptSolve does before iterating). */
+cuopt_int_t cuOptB200SolverInitialise(cuOptB200Solver solver);
+/* Run the outer loop for `accepted_steps` more accepted PDLP iterations (<0: to termination).
+ * *finished_ptr = 1 once a termination status was reached. */
+cuopt_int_t cuOptB200SolverAdvance(cuOptB200Solver solver, cuopt_int_t accepted_steps, cuopt_int_t* finished_ptr);
+/* Named state: scalars "step_size", "primal_weight", "tau", "sigma", "sum_w", "k_total", "k_pdhg",
+ * "its_since_restart", "interaction", "norm_dx2", "norm_dy2", "l2_norm_b", "l2_norm_c", "n_restarts";
+ * vectors "x", "y", "aty", "x_next", "y_next", "aty_next", "x_bar", "sum_x", "sum_y", "x_avg", "y_avg",
+ * "row_scaling", "col_scaling", "scaled_values", "scaled_values_t", "scaled_c", "scaled_l", "scaled_u",
+ * "scaled_lc", "scaled_uc", "x_last_restart", "y_last_restart" (scaled space unless noted). */
+cuopt_int_t cuOptB200SolverGetScalar(cuOptB200Solver solver, const char* name, cuopt_float_t* value_ptr);
+cuopt_int_t cuOptB200SolverGetVector(cuOptB200Solver solver,
+                                     const char* name,
+                                     cuopt_float_t* values,
+                                     cuopt_int_t capacity,
+                                     cuopt_int_t* size_ptr);
+/* Solution object (same type cuOptSolve returns) of a finished session. */
+cuopt_int_t cuOptB200SolverGetSolution(cuOptB200Solver solver, cuOptSolution* solution_ptr);
+/* Time the three PDHG kernels in situ (CUDA events on the solver's stream) after `warmup_steps`. */
+cuopt_int_t cuOptB200SolverProfileKernels(cuOptB200Solver solver,
+                                          cuopt_int_t warmup_steps,
+                                          cuopt_int_t reps,
+                                          cuOptB200KernelProfile* profile);
+
+/* cuOptReadProblem with an explicit format switch (the reference C ABI always parses free format;
+ * its C++ parse_mps(file, fixed_mps_format) has the flag: cpp/libmps_parser/include/mps_parser/parser.hpp:33). */
+cuopt_int_t cuOptB200ReadProblem(const char* filename, cuopt_int_t fixed_format, cuOptOptimizationProblem* problem_ptr);
+
+/* Library identification: "cuopt-b200 <version> sm_100a". */
+const char* cuOptB200Version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CUOPT_B200_EXT_H */

@@ -174,8 +174,8 @@ class Oracle:
             C.byref(self.settings)))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().pdlp_oracle_destroy(self.h)
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.pdlp_oracle_destroy(self.h)
             self.h = None
 
     def initialise(self):
