@@ -34,18 +34,24 @@ class dvec {
   explicit dvec(size_t n) { resize(n); }
   dvec(const dvec&)            = delete;
   dvec& operator=(const dvec&) = delete;
-  dvec(dvec&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  dvec(dvec&& o) noexcept : p_(o.p_), n_(o.n_), slack_(o.slack_) { o.p_ = nullptr; o.n_ = 0; }
   dvec& operator=(dvec&& o) noexcept
   {
-    if (this != &o) { release(); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+    if (this != &o) { release(); p_ = o.p_; n_ = o.n_; slack_ = o.slack_; o.p_ = nullptr; o.n_ = 0; }
     return *this;
   }
   ~dvec() { release(); }
-  void resize(size_t n)
+  // `slack` extra elements are allocated (zero-filled) past the logical size: the 16-byte granular bulk
+  // copies of the SpMV pipeline may read a few elements beyond the end of idx / val / off.
+  void resize(size_t n, size_t slack = 0)
   {
     release();
-    n_ = n;
-    if (n) CUOPT_CUDA_TRY(cudaMalloc(&p_, std::max<size_t>(n, 1) * sizeof(T)));
+    n_     = n;
+    slack_ = slack;
+    if (n + slack) {
+      CUOPT_CUDA_TRY(cudaMalloc(&p_, (n + slack) * sizeof(T)));
+      if (slack) CUOPT_CUDA_TRY(cudaMemset(p_ + n, 0, slack * sizeof(T)));
+    }
   }
   void release()
   {
@@ -53,12 +59,12 @@ class dvec {
     p_ = nullptr;
     n_ = 0;
   }
-  void upload(const T* h, size_t n, cudaStream_t s)
+  void upload(const T* h, size_t n, cudaStream_t s, size_t slack = 0)
   {
-    if (n_ != n) resize(n);
+    if (n_ != n || slack_ != slack) resize(n, slack);
     if (n) CUOPT_CUDA_TRY(cudaMemcpyAsync(p_, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
   }
-  void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+  void upload(const std::vector<T>& h, cudaStream_t s, size_t slack = 0) { upload(h.data(), h.size(), s, slack); }
   void download(T* h, cudaStream_t s) const
   {
     if (n_) CUOPT_CUDA_TRY(cudaMemcpyAsync(h, p_, n_ * sizeof(T), cudaMemcpyDeviceToHost, s));
@@ -69,7 +75,7 @@ class dvec {
   }
   void copy_from(const dvec& o, cudaStream_t s)
   {
-    if (n_ != o.n_) resize(o.n_);
+    if (n_ != o.n_ || slack_ != o.slack_) resize(o.n_, o.slack_);
     if (n_) CUOPT_CUDA_TRY(cudaMemcpyAsync(p_, o.p_, n_ * sizeof(T), cudaMemcpyDeviceToDevice, s));
   }
   T* data() { return p_; }
@@ -77,8 +83,9 @@ class dvec {
   size_t size() const { return n_; }
 
  private:
-  T* p_     = nullptr;
-  size_t n_ = 0;
+  T* p_         = nullptr;
+  size_t n_     = 0;
+  size_t slack_ = 0;
 };
 
 // ---- device-side helpers ---------------------------------------------------------------------

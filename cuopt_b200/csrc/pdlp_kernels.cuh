@@ -21,27 +21,16 @@
 #pragma once
 
 #include "device_utils.cuh"
+#include "spmv_pipeline.cuh"
+#include "spmv_warp.cuh"
 
 #include <math_constants.h>
 
 namespace cuopt_b200 {
 
-constexpr int SPMV_THREADS = 256;
-constexpr int SPMV_NNZ     = 2048;  // nonzeros per row block (8 per thread)
-constexpr int SPMV_ROWS    = 2048;  // max rows per row block
-constexpr int SPMV_PADDED  = SPMV_NNZ + (SPMV_NNZ >> 3);
-__host__ __device__ constexpr int spmv_pad(int e) { return e + (e >> 3); }
-
-constexpr int EW_THREADS = 256;  // element-wise kernels
-
-struct csr_view_t {
-  int rows;
-  const int* off;
-  const int* idx;
-  const double* val;
-  int n_blocks;
-  const int4* blk;  // {first row, one-past-last row, first nnz, one-past-last nnz}
-};
+constexpr int EW_THREADS  = 256;  // element-wise kernels
+constexpr int PDHG_MIN_CTAS = 6;  // hot SpMV kernels: <= 40 registers, 6 x 256 threads per SM (measured optimum)
+constexpr int EVAL_STAGES = 3;    // two-vector evaluation kernels
 
 // Device-resident control block: every scalar the PDHG loop reads or writes.
 struct pdhg_ctl_t {
@@ -76,89 +65,6 @@ struct eval_consts_t {
   double l2_norm_b, l2_norm_c;
   int reduced_cost_rule;  // 1: handle_some_primal_gradients_on_finite_bounds_as_residuals
 };
-
-// ---------------------------------------------------------------------------------------------
-// Row-block SpMV core.  NV vectors are multiplied in the same pass over the matrix.
-// row_op(row, sums[NV]) is called exactly once per row of the block by one thread.
-// `prod` is NV x SPMV_PADDED doubles of shared memory, `red` >= 32 doubles.
-// ---------------------------------------------------------------------------------------------
-template <int NV, typename RowOp>
-__device__ __forceinline__ void spmv_row_block(const csr_view_t& A,
-                                               const int4 d,
-                                               const double* const* x,
-                                               double* prod,
-                                               double* red,
-                                               RowOp& row_op)
-{
-  const int tid = threadIdx.x;
-  const int r0 = d.x, r1 = d.y, lo = d.z, hi = d.w;
-  if (hi - lo > SPMV_NNZ) {
-    // one long row: strided partial sums, then the fixed block tree
-    double acc[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = 0.0;
-    for (int e = lo + tid; e < hi; e += SPMV_THREADS) {
-      const int c    = ld_stream(A.idx + e);
-      const double a = ld_stream(A.val + e);
-#pragma unroll
-      for (int v = 0; v < NV; ++v) acc[v] += a * __ldg(x[v] + c);
-    }
-    double s[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) s[v] = block_reduce(acc[v], red);
-    if (tid == 0) row_op(r0, s);
-    __syncthreads();
-    return;
-  }
-  // row extents first: their latency overlaps the staging phase
-  int rs[SPMV_ROWS / SPMV_THREADS], re[SPMV_ROWS / SPMV_THREADS];
-#pragma unroll
-  for (int k = 0; k < SPMV_ROWS / SPMV_THREADS; ++k) {
-    const int r = r0 + tid + k * SPMV_THREADS;
-    if (r < r1) {
-      rs[k] = __ldg(A.off + r) - lo;
-      re[k] = __ldg(A.off + r + 1) - lo;
-    }
-  }
-  // stage products: all index loads, then all value loads + gathers (8 independent chains per thread)
-  int col[SPMV_NNZ / SPMV_THREADS];
-  double a[SPMV_NNZ / SPMV_THREADS];
-#pragma unroll
-  for (int k = 0; k < SPMV_NNZ / SPMV_THREADS; ++k) {
-    const int e = lo + tid + k * SPMV_THREADS;
-    col[k]      = (e < hi) ? ld_stream(A.idx + e) : -1;
-  }
-#pragma unroll
-  for (int k = 0; k < SPMV_NNZ / SPMV_THREADS; ++k) {
-    const int e = lo + tid + k * SPMV_THREADS;
-    a[k]        = (e < hi) ? ld_stream(A.val + e) : 0.0;
-  }
-#pragma unroll
-  for (int k = 0; k < SPMV_NNZ / SPMV_THREADS; ++k) {
-    if (col[k] >= 0) {
-      const int p = spmv_pad(tid + k * SPMV_THREADS);
-#pragma unroll
-      for (int v = 0; v < NV; ++v) prod[v * SPMV_PADDED + p] = a[k] * __ldg(x[v] + col[k]);
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < SPMV_ROWS / SPMV_THREADS; ++k) {
-    const int r = r0 + tid + k * SPMV_THREADS;
-    if (r < r1) {
-      double s[NV];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) s[v] = 0.0;
-      for (int p = rs[k]; p < re[k]; ++p) {
-        const int q = spmv_pad(p);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) s[v] += prod[v * SPMV_PADDED + q];
-      }
-      row_op(r, s);
-    }
-  }
-  __syncthreads();
-}
 
 // Publish per-CTA partial sums and elect the last CTA to finish (returns true in every thread of
 // that CTA).  `parts` is NQ x gridDim.x doubles; the elected CTA reads them back in a fixed order.
@@ -232,18 +138,18 @@ __global__ void __launch_bounds__(EW_THREADS) k_primal_step(const pdhg_ctl_t* __
 // K2 — A*xbar and dual step.  y' = max(ybar + sigma lc, min(ybar + sigma uc, 0)), ybar = y - sigma (A xbar)
 // (pdhg.cu:73-117 + utils.cuh:98-112) + dual half of the running average + partial ||dy||^2.
 // =============================================================================================
-__global__ void __launch_bounds__(SPMV_THREADS) k_dual_step(const pdhg_ctl_t* __restrict__ ctl,
-                                                            csr_view_t A,
-                                                            const double* __restrict__ xbar,
-                                                            double* __restrict__ ybuf0,
-                                                            double* __restrict__ ybuf1,
-                                                            const double* __restrict__ lc,
-                                                            const double* __restrict__ uc,
-                                                            double* __restrict__ sum_y,
-                                                            double* __restrict__ part_dy2)
+__global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_dual_step(const pdhg_ctl_t* __restrict__ ctl,
+                                                                           csr_warp_view_t A,
+                                                                           const double* __restrict__ xbar,
+                                                                           double* __restrict__ ybuf0,
+                                                                           double* __restrict__ ybuf1,
+                                                                           const double* __restrict__ lc,
+                                                                           const double* __restrict__ uc,
+                                                                           double* __restrict__ sum_y,
+                                                                           double* __restrict__ part_dy2)
 {
   if (!ctl->active) return;
-  __shared__ double prod[SPMV_PADDED];
+  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
   __shared__ double red[32];
   const int cur      = ctl->parity;
   const double* y    = cur ? ybuf1 : ybuf0;
@@ -252,20 +158,28 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_dual_step(const pdhg_ctl_t* __
   const bool pending = ctl->pending_avg != 0;
   const double w     = ctl->pending_weight;
   double dy2         = 0.0;
-  auto row_op        = [&](int i, const double (&s)[1]) {
-    const double yi = y[i];
-    if (pending) sum_y[i] = sum_y[i] + w * yi;
-    double next      = yi - (sigma * s[0]);
-    const double low = next + sigma * ld_stream(lc + i);
-    const double up  = next + sigma * ld_stream(uc + i);
+  struct payload_t {
+    double y, lc, uc, sum;
+  };
+  auto pre_op = [&](int i) {
+    payload_t p;
+    p.y   = y[i];
+    p.lc  = ld_stream(lc + i);
+    p.uc  = ld_stream(uc + i);
+    p.sum = pending ? sum_y[i] : 0.0;
+    return p;
+  };
+  auto row_op = [&](int i, double s, const payload_t& p) {
+    if (pending) sum_y[i] = p.sum + w * p.y;
+    double next      = p.y - (sigma * s);
+    const double low = next + sigma * p.lc;
+    const double up  = next + sigma * p.uc;
     next             = fmax(low, fmin(up, 0.0));
     yn[i]            = next;
-    const double d   = next - yi;
+    const double d   = next - p.y;
     dy2 += d * d;
   };
-  const double* xs[1] = {xbar};
-  for (int b = blockIdx.x; b < A.n_blocks; b += gridDim.x)
-    spmv_row_block<1>(A, __ldg(A.blk + b), xs, prod, red, row_op);
+  spmv_warp_rows<payload_t>(A, xbar, prod[threadIdx.x >> 5], pre_op, row_op);
   const double tot = block_reduce(dy2, red);
   if (threadIdx.x == 0) part_dy2[blockIdx.x] = tot;
 }
@@ -275,20 +189,20 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_dual_step(const pdhg_ctl_t* __
 // adaptive step-size rule with accept/reject (adaptive_step_size_strategy.cu:92-188, 232-345).
 // interaction = dx . (A^T y' - A^T y)  (the reference's SpMV-saving form, :267-277).
 // =============================================================================================
-__global__ void __launch_bounds__(SPMV_THREADS) k_transpose_step(pdhg_ctl_t* __restrict__ ctl,
-                                                                 csr_view_t AT,
-                                                                 const double* __restrict__ ybuf0,
-                                                                 const double* __restrict__ ybuf1,
-                                                                 const double* __restrict__ xbuf0,
-                                                                 const double* __restrict__ xbuf1,
-                                                                 double* __restrict__ aty0,
-                                                                 double* __restrict__ aty1,
-                                                                 double* __restrict__ parts,  // 2 x gridDim.x
-                                                                 const double* __restrict__ part_dy2,
-                                                                 int n_part_dy2)
+__global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_step(pdhg_ctl_t* __restrict__ ctl,
+                                                                                csr_warp_view_t AT,
+                                                                                const double* __restrict__ ybuf0,
+                                                                                const double* __restrict__ ybuf1,
+                                                                                const double* __restrict__ xbuf0,
+                                                                                const double* __restrict__ xbuf1,
+                                                                                double* __restrict__ aty0,
+                                                                                double* __restrict__ aty1,
+                                                                                double* __restrict__ parts,  // 2 x gridDim.x
+                                                                                const double* __restrict__ part_dy2,
+                                                                                int n_part_dy2)
 {
   if (!ctl->active) return;
-  __shared__ double prod[SPMV_PADDED];
+  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
   __shared__ double red[32];
   const int cur     = ctl->parity;
   const double* yn  = cur ? ybuf0 : ybuf1;  // candidate y'
@@ -297,15 +211,21 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_transpose_step(pdhg_ctl_t* __r
   const double* aty = cur ? aty1 : aty0;
   double* atyn      = cur ? aty0 : aty1;
   double acc[2]     = {0.0, 0.0};  // interaction, ||dx||^2
-  auto row_op       = [&](int j, const double (&s)[1]) {
-    atyn[j]        = s[0];
-    const double d = xn[j] - x[j];
-    acc[0] += d * (s[0] - aty[j]);
-    acc[1] += d * d;
+  struct payload_t {
+    double dx, aty;
   };
-  const double* ys[1] = {yn};
-  for (int b = blockIdx.x; b < AT.n_blocks; b += gridDim.x)
-    spmv_row_block<1>(AT, __ldg(AT.blk + b), ys, prod, red, row_op);
+  auto pre_op = [&](int j) {
+    payload_t p;
+    p.dx  = xn[j] - x[j];
+    p.aty = aty[j];
+    return p;
+  };
+  auto row_op = [&](int j, double s, const payload_t& p) {
+    atyn[j] = s;
+    acc[0] += p.dx * (s - p.aty);
+    acc[1] += p.dx * p.dx;
+  };
+  spmv_warp_rows<payload_t>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op);
 
   if (!publish_and_elect<2>(acc, parts, &ctl->ticket[0], red)) return;
   const double interaction = gather_partials(parts, gridDim.x, red);
@@ -382,14 +302,15 @@ __global__ void k_begin_batch(pdhg_ctl_t* ctl, int steps)
 }
 
 // Plain y = A x on the row-block scheme (A^T y after a restart to the average, pdhg.cu:120-134).
-__global__ void __launch_bounds__(SPMV_THREADS) k_spmv(csr_view_t A, const double* __restrict__ x, double* __restrict__ out)
+__global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_spmv(csr_warp_view_t A,
+                                                                      const double* __restrict__ x,
+                                                                      double* __restrict__ out)
 {
-  __shared__ double prod[SPMV_PADDED];
-  __shared__ double red[32];
-  auto row_op         = [&](int i, const double (&s)[1]) { out[i] = s[0]; };
-  const double* xs[1] = {x};
-  for (int b = blockIdx.x; b < A.n_blocks; b += gridDim.x)
-    spmv_row_block<1>(A, __ldg(A.blk + b), xs, prod, red, row_op);
+  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
+  struct payload_t {};
+  auto pre_op = [&](int) { return payload_t{}; };
+  auto row_op = [&](int i, double s, const payload_t&) { out[i] = s; };
+  spmv_warp_rows<payload_t>(A, x, prod[threadIdx.x >> 5], pre_op, row_op);
 }
 
 // =============================================================================================
@@ -415,12 +336,17 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_eval_rows(csr_view_t A,
                                                             const double* __restrict__ uc,
                                                             double* __restrict__ parts)
 {
-  __shared__ double prod[2 * SPMV_PADDED];
-  __shared__ double red[32];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto& sm      = *reinterpret_cast<spmv_smem_t<2, EVAL_STAGES>*>(smem_raw);
+  double* red   = sm.red;
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  auto row_op   = [&](int i, const double (&s)[2]) {
-    const double lo = lc[i], hi = uc[i];
-    const double yv[2] = {y_cur[i], y_avg[i]};
+  struct payload_t {
+    double lo, hi, y0, y1;
+  };
+  auto pre_op = [&](int i) { return payload_t{lc[i], uc[i], y_cur[i], y_avg[i]}; };
+  auto row_op = [&](int i, const double (&s)[2], const payload_t& p) {
+    const double lo = p.lo, hi = p.hi;
+    const double yv[2] = {p.y0, p.y1};
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       // utils.cuh:166-178
@@ -431,8 +357,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_eval_rows(csr_view_t A,
     }
   };
   const double* xs[2] = {x_cur, x_avg};
-  for (int b = blockIdx.x; b < A.n_blocks; b += gridDim.x)
-    spmv_row_block<2>(A, __ldg(A.blk + b), xs, prod, red, row_op);
+  spmv_pipeline<2, EVAL_STAGES, payload_t>(A, xs, sm, pre_op, row_op);
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
     const double t = block_reduce(acc[q], red);
@@ -459,12 +384,17 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_eval_cols(pdhg_ctl_t* __restri
                                                             eval_consts_t k,
                                                             eval_t* __restrict__ out)  // out[0] current, out[1] average
 {
-  __shared__ double prod[2 * SPMV_PADDED];
-  __shared__ double red[32];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto& sm      = *reinterpret_cast<spmv_smem_t<2, EVAL_STAGES>*>(smem_raw);
+  double* red   = sm.red;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  auto row_op   = [&](int j, const double (&s)[2]) {
-    const double cj = c[j], lo = l[j], hi = u[j];
-    const double xv[2] = {x_cur[j], x_avg[j]};
+  struct payload_t {
+    double c, lo, hi, x0, x1;
+  };
+  auto pre_op = [&](int j) { return payload_t{c[j], l[j], u[j], x_cur[j], x_avg[j]}; };
+  auto row_op = [&](int j, const double (&s)[2], const payload_t& p) {
+    const double cj = p.c, lo = p.lo, hi = p.hi;
+    const double xv[2] = {p.x0, p.x1};
     double* rcs[2]     = {rc_cur, rc_avg};
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
@@ -483,8 +413,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_eval_cols(pdhg_ctl_t* __restri
     }
   };
   const double* ys[2] = {y_cur, y_avg};
-  for (int b = blockIdx.x; b < AT.n_blocks; b += gridDim.x)
-    spmv_row_block<2>(AT, __ldg(AT.blk + b), ys, prod, red, row_op);
+  spmv_pipeline<2, EVAL_STAGES, payload_t>(AT, ys, sm, pre_op, row_op);
 
   if (!publish_and_elect<8>(acc, parts, &ctl->ticket[1], red)) return;
   double tot[14];

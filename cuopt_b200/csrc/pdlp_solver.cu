@@ -30,19 +30,24 @@ namespace cuopt_b200 {
 namespace {
 
 struct csr_dev_t {
-  int rows = 0, cols = 0, nnz = 0, n_blocks = 0;
+  int rows = 0, cols = 0, nnz = 0, n_blocks = 0, n_wb = 0;
   dvec<int> off, idx;
   dvec<double> val;
-  dvec<int4> blk;
+  dvec<int4> blk;    // CTA row blocks (TMA pipeline of the evaluation kernels)
+  dvec<int2> wdesc;  // warp row blocks (hot PDHG kernels)
   const csr_dev_t* structure = nullptr;  // scaled copies share offsets / indices / row blocks with the original
   const int* off_ptr() const { return structure ? structure->off.data() : off.data(); }
   const int* idx_ptr() const { return structure ? structure->idx.data() : idx.data(); }
   const int4* blk_ptr() const { return structure ? structure->blk.data() : blk.data(); }
   csr_view_t view() const { return csr_view_t{rows, off_ptr(), idx_ptr(), val.data(), n_blocks, blk_ptr()}; }
+  csr_warp_view_t warp_view() const
+  {
+    return csr_warp_view_t{off_ptr(), idx_ptr(), val.data(), n_wb, structure ? structure->wdesc.data() : wdesc.data()};
+  }
   // same sparsity pattern, own values (device-to-device copy)
   void alias_structure_copy_values(const csr_dev_t& o, cudaStream_t s)
   {
-    rows = o.rows; cols = o.cols; nnz = o.nnz; n_blocks = o.n_blocks;
+    rows = o.rows; cols = o.cols; nnz = o.nnz; n_blocks = o.n_blocks; n_wb = o.n_wb;
     structure = &o;
     val.copy_from(o.val, s);
   }
@@ -68,18 +73,43 @@ std::vector<int4> build_row_blocks(const std::vector<int>& off)
   return blocks;
 }
 
+// Warp row blocks for the hot kernels: consecutive rows with <= WARP_NNZ nonzeros and <= 32 rows; a longer row is a
+// block of its own.  Returns n_wb + 1 descriptors {first row, first nnz}.
+std::vector<int2> build_warp_blocks(const std::vector<int>& off)
+{
+  std::vector<int2> wd;
+  const int rows = (int)off.size() - 1;
+  int r          = 0;
+  while (r < rows) {
+    const int lo = off[r];
+    int r1       = r;
+    if (off[r + 1] - lo > WARP_NNZ) {
+      r1 = r + 1;
+    } else {
+      while (r1 < rows && off[r1 + 1] - lo <= WARP_NNZ && (r1 - r) < 32) ++r1;
+    }
+    wd.push_back(make_int2(r, lo));
+    r = r1;
+  }
+  wd.push_back(make_int2(rows, off[rows]));
+  return wd;
+}
+
 void upload_csr(csr_dev_t& d, int rows, int cols, const std::vector<int>& off, const std::vector<int>& idx,
                 const std::vector<double>& val, cudaStream_t s)
 {
   d.rows = rows;
   d.cols = cols;
   d.nnz  = (int)val.size();
-  d.off.upload(off, s);
-  d.idx.upload(idx, s);
-  d.val.upload(val, s);
+  d.off.upload(off, s, SPMV_TAIL_SLACK);
+  d.idx.upload(idx, s, SPMV_TAIL_SLACK);
+  d.val.upload(val, s, SPMV_TAIL_SLACK);
   auto blocks = build_row_blocks(off);
   d.n_blocks  = (int)blocks.size();
   d.blk.upload(blocks, s);
+  auto wblocks = build_warp_blocks(off);
+  d.n_wb       = (int)wblocks.size() - 1;
+  d.wdesc.upload(wblocks, s);
 }
 
 // Stable CSR transpose on the host (row indices ascending inside each transposed row — the order
@@ -101,6 +131,9 @@ void transpose_host(int rows, int cols, const std::vector<int>& off, const std::
       tval[q]     = val[p];
     }
 }
+
+
+constexpr size_t SMEM_EVAL = sizeof(spmv_smem_t<2, EVAL_STAGES>);
 
 int ew_grid(int n, int sms) { return std::max(1, std::min((n + EW_THREADS - 1) / EW_THREADS, sms * 8)); }
 
@@ -131,6 +164,7 @@ struct pdlp_solver_t::impl_t {
   pdhg_ctl_t* h_ctl = nullptr;  // pinned mirrors
   eval_t* h_eval    = nullptr;
   double* h_scalar  = nullptr;
+  int grid_sp = 1;
   int grid_k1 = 1, grid_k2 = 1, grid_k3 = 1, grid_er = 1, grid_ec = 1, grid_n = 1, grid_m = 1, grid_misc = 1;
   std::map<int, cudaGraphExec_t> graphs;
   bool use_graphs = true;
@@ -223,15 +257,23 @@ struct pdlp_solver_t::impl_t {
     Dc.resize(n);
 
     // persistent grids: one wave of resident CTAs
-    auto occ_grid = [&](const void* kernel, int blocks) {
+    auto occ_grid = [&](const void* kernel, int blocks, size_t smem) {
+      CUOPT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 1;
-      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPMV_THREADS, 0));
+      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPMV_THREADS, smem));
       return std::max(1, std::min(blocks, sms * std::max(per_sm, 1)));
     };
-    grid_k2   = occ_grid((const void*)k_dual_step, As.n_blocks);
-    grid_k3   = occ_grid((const void*)k_transpose_step, ATs.n_blocks);
-    grid_er   = occ_grid((const void*)k_eval_rows, A.n_blocks);
-    grid_ec   = occ_grid((const void*)k_eval_cols, AT.n_blocks);
+    auto warp_grid = [&](const void* kernel, int n_wb) {
+      int per_sm = 1;
+      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARP_THREADS, 0));
+      const int ctas = (n_wb + WARP_PER_CTA - 1) / WARP_PER_CTA;
+      return std::max(1, std::min(ctas, sms * std::max(per_sm, 1)));
+    };
+    grid_k2   = warp_grid((const void*)k_dual_step, As.n_wb);
+    grid_k3   = warp_grid((const void*)k_transpose_step, ATs.n_wb);
+    grid_sp   = warp_grid((const void*)k_spmv, ATs.n_wb);
+    grid_er   = occ_grid((const void*)k_eval_rows, A.n_blocks, SMEM_EVAL);
+    grid_ec   = occ_grid((const void*)k_eval_cols, AT.n_blocks, SMEM_EVAL);
     grid_n    = ew_grid(n, sms);
     grid_m    = ew_grid(m, sms);
     grid_k1   = grid_n;
@@ -360,9 +402,9 @@ struct pdlp_solver_t::impl_t {
     k_primal_step<<<grid_k1, EW_THREADS, 0, stream>>>(d_ctl.data(), n, xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
                                                       atybuf[1].data(), cs.data(), ls.data(), us.data(), sum_x.data(),
                                                       xbar.data());
-    k_dual_step<<<grid_k2, SPMV_THREADS, 0, stream>>>(d_ctl.data(), As.view(), xbar.data(), ybuf[0].data(), ybuf[1].data(),
+    k_dual_step<<<grid_k2, WARP_THREADS, 0, stream>>>(d_ctl.data(), As.warp_view(), xbar.data(), ybuf[0].data(), ybuf[1].data(),
                                                       lcs.data(), ucs.data(), sum_y.data(), part_dy2.data());
-    k_transpose_step<<<grid_k3, SPMV_THREADS, 0, stream>>>(d_ctl.data(), ATs.view(), ybuf[0].data(), ybuf[1].data(),
+    k_transpose_step<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
                                                            xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
                                                            atybuf[1].data(), part_k3.data(), part_dy2.data(), grid_k2);
   }
@@ -403,7 +445,7 @@ struct pdlp_solver_t::impl_t {
     CUOPT_CUDA_TRY(cudaEventRecord(ev_a, stream));
     if (need_aty) {  // pdhg.cu:183-202
       const int cur = h_ctl->parity;
-      k_spmv<<<grid_k3, SPMV_THREADS, 0, stream>>>(ATs.view(), ybuf[cur].data(), atybuf[cur].data());
+      k_spmv<<<grid_sp, WARP_THREADS, 0, stream>>>(ATs.warp_view(), ybuf[cur].data(), atybuf[cur].data());
       ++launches;
       need_aty = false;
     }
@@ -456,9 +498,9 @@ struct pdlp_solver_t::impl_t {
                                                              x_avg.data(), Dc.data());
     k_average_and_unscale<<<grid_m, EW_THREADS, 0, stream>>>(d_ctl.data(), mode, m, ybuf[cur].data(), sum_y.data(),
                                                              y_avg.data(), Dr.data());
-    k_eval_rows<<<grid_er, SPMV_THREADS, 0, stream>>>(A.view(), xbuf[cur].data(), x_avg.data(), ybuf[cur].data(),
+    k_eval_rows<<<grid_er, SPMV_THREADS, SMEM_EVAL, stream>>>(A.view(), xbuf[cur].data(), x_avg.data(), ybuf[cur].data(),
                                                       y_avg.data(), lc.data(), uc.data(), part_rows.data());
-    k_eval_cols<<<grid_ec, SPMV_THREADS, 0, stream>>>(d_ctl.data(), AT.view(), xbuf[cur].data(), x_avg.data(),
+    k_eval_cols<<<grid_ec, SPMV_THREADS, SMEM_EVAL, stream>>>(d_ctl.data(), AT.view(), xbuf[cur].data(), x_avg.data(),
                                                       ybuf[cur].data(), y_avg.data(), c.data(), l.data(), u.data(),
                                                       rc_cur.data(), rc_avg.data(), part_cols.data(), part_rows.data(),
                                                       grid_er, eval_consts(), d_eval.data());
@@ -773,11 +815,11 @@ kernel_profile_t pdlp_solver_t::profile_kernels(int warmup_steps, int reps)
                                                           s.atybuf[0].data(), s.atybuf[1].data(), s.cs.data(), s.ls.data(),
                                                           s.us.data(), s.sum_x.data(), s.xbar.data());
     cudaEventRecord(ev[1], s.stream);
-    k_dual_step<<<s.grid_k2, SPMV_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.As.view(), s.xbar.data(), s.ybuf[0].data(),
+    k_dual_step<<<s.grid_k2, WARP_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.As.warp_view(), s.xbar.data(), s.ybuf[0].data(),
                                                           s.ybuf[1].data(), s.lcs.data(), s.ucs.data(), s.sum_y.data(),
                                                           s.part_dy2.data());
     cudaEventRecord(ev[2], s.stream);
-    k_transpose_step<<<s.grid_k3, SPMV_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.ATs.view(), s.ybuf[0].data(),
+    k_transpose_step<<<s.grid_k3, WARP_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.ATs.warp_view(), s.ybuf[0].data(),
                                                                s.ybuf[1].data(), s.xbuf[0].data(), s.xbuf[1].data(),
                                                                s.atybuf[0].data(), s.atybuf[1].data(), s.part_k3.data(),
                                                                s.part_dy2.data(), s.grid_k2);
