@@ -12,8 +12,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libcuopt.so")
 
-CU_SOURCES = ["pdlp_solver.cu"]
-CPP_SOURCES = ["c_api.cpp", "mps_reader.cpp", "solver_settings.cpp"]
+CU_SOURCES = ["pdlp_solver.cu", "csr_transpose.cu"]
+CPP_SOURCES = ["c_api.cpp", "mps_reader.cpp", "solver_settings.cpp", "dist_comm.cpp"]
 
 
 def nvcc_path() -> str:
@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd += ["-ccbin", host_cxx]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += sources() + ["-o", LIB, "-Xlinker", "-soname,libcuopt.so"]
+    cmd += sources() + ["-o", LIB, "-Xlinker", "-soname,libcuopt.so", "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

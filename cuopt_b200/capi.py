@@ -65,7 +65,8 @@ REFERENCE_SYMBOLS = [
 EXTENSION_SYMBOLS = [
     "cuOptB200GetLPStats", "cuOptB200SolverCreate", "cuOptB200SolverDestroy", "cuOptB200SolverInitialise",
     "cuOptB200SolverAdvance", "cuOptB200SolverGetScalar", "cuOptB200SolverGetVector", "cuOptB200SolverGetSolution",
-    "cuOptB200SolverProfileKernels", "cuOptB200ReadProblem", "cuOptB200Version",
+    "cuOptB200SolverProfileKernels", "cuOptB200ReadProblem", "cuOptB200Version", "cuOptB200DistGetUniqueId",
+    "cuOptB200DistInit", "cuOptB200DistDestroy", "cuOptB200SolveDistributed",
 ]
 
 _lib = None
@@ -139,6 +140,11 @@ def lib():
         L.cuOptB200SolverProfileKernels.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(KernelProfile)]
         L.cuOptB200ReadProblem.argtypes = [C.c_char_p, C.c_int32, C.POINTER(vp)]
         L.cuOptB200Version.restype = C.c_char_p
+        L.cuOptB200DistGetUniqueId.argtypes = [C.c_char_p]
+        L.cuOptB200DistInit.argtypes = [C.c_int32, C.c_int32, C.c_char_p, C.POINTER(vp)]
+        L.cuOptB200DistDestroy.argtypes = [C.POINTER(vp)]
+        L.cuOptB200DistDestroy.restype = None
+        L.cuOptB200SolveDistributed.argtypes = [vp, vp, vp, C.POINTER(vp)]
         _lib = L
     return _lib
 
@@ -416,3 +422,30 @@ class Solver:
         p = KernelProfile()
         _check(lib().cuOptB200SolverProfileKernels(self.h, warmup_steps, reps, C.byref(p)))
         return p
+
+
+class Dist:
+    """cuOptB200Dist communicator (one per process / GPU)."""
+
+    def __init__(self, rank: int, world: int, unique_id: bytes):
+        self.rank, self.world = rank, world
+        self.h = C.c_void_p()
+        _check(lib().cuOptB200DistInit(rank, world, unique_id, C.byref(self.h)), "cuOptB200DistInit")
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().cuOptB200DistGetUniqueId(buf), "cuOptB200DistGetUniqueId")
+        return buf.raw
+
+    def close(self):
+        if self.h and _lib is not None:
+            _lib.cuOptB200DistDestroy(C.byref(self.h))
+
+    __del__ = close
+
+
+def solve_distributed(local_problem: Problem, settings: Settings, dist: Dist) -> Solution:
+    h = C.c_void_p()
+    rc = lib().cuOptB200SolveDistributed(local_problem.h, settings.h, dist.h, C.byref(h))
+    return Solution(h, local_problem.num_constraints, local_problem.num_variables, rc)

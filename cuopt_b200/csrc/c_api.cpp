@@ -2,6 +2,7 @@
 // Semantics follow cpp/src/linear_programming/cuopt_c.cpp of the reference (line tags below).
 #include <cuopt_b200/cuopt_b200_ext.h>
 
+#include "dist_comm.hpp"
 #include "lp_problem.hpp"
 #include "pdlp_solver.hpp"
 #include "solver_settings.hpp"
@@ -602,6 +603,48 @@ cuopt_int_t cuOptB200SolverProfileKernels(cuOptB200Solver solver,
     profile->grid_transpose       = k.grid_transpose;
   });
   return CUOPT_SUCCESS;
+}
+
+cuopt_int_t cuOptB200DistGetUniqueId(char* unique_id_128_bytes)
+{
+  if (unique_id_128_bytes == nullptr) return CUOPT_INVALID_ARGUMENT;
+  SOLVER_GUARD(dist_get_unique_id(unique_id_128_bytes));
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptB200DistInit(cuopt_int_t rank, cuopt_int_t world_size, const char* unique_id_128_bytes, cuOptB200Dist* dist_ptr)
+{
+  if (unique_id_128_bytes == nullptr || dist_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  *dist_ptr = nullptr;
+  SOLVER_GUARD(*dist_ptr = dist_create(rank, world_size, unique_id_128_bytes));
+  return CUOPT_SUCCESS;
+}
+void cuOptB200DistDestroy(cuOptB200Dist* dist_ptr)
+{
+  if (dist_ptr == nullptr || *dist_ptr == nullptr) return;
+  dist_destroy(static_cast<dist_context_t*>(*dist_ptr));
+  *dist_ptr = nullptr;
+}
+cuopt_int_t cuOptB200SolveDistributed(cuOptOptimizationProblem local_rows_problem,
+                                      cuOptSolverSettings settings,
+                                      cuOptB200Dist dist,
+                                      cuOptSolution* solution_ptr)
+{
+  if (local_rows_problem == nullptr || settings == nullptr || dist == nullptr || solution_ptr == nullptr)
+    return CUOPT_INVALID_ARGUMENT;
+  const lp_problem_t& p       = *static_cast<const lp_problem_t*>(local_rows_problem);
+  const solver_settings_t& ss = *static_cast<const solver_settings_t*>(settings);
+  auto* h                     = new (std::nothrow) solution_handle_t();
+  if (!h) return CUOPT_OUT_OF_MEMORY;
+  if (p.is_mip()) {
+    h->sol.error_status  = CUOPT_VALIDATION_ERROR;
+    h->sol.error_message = "cuopt-b200 implements the LP (PDLP) path only; the problem declares integer variables";
+  } else {
+    auto* d = static_cast<dist_context_t*>(dist);
+    h->sol  = solve_lp(p, ss.pdlp(), d);
+    if (h->sol.error_status == 0 && d->rank == 0) log_solution(ss.pdlp(), p, h->sol);
+  }
+  *solution_ptr = h;
+  return h->sol.error_status;
 }
 
 cuopt_int_t cuOptB200ReadProblem(const char* filename, cuopt_int_t fixed_format, cuOptOptimizationProblem* problem_ptr)

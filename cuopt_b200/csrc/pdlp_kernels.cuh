@@ -96,6 +96,52 @@ __device__ __forceinline__ double gather_partials(const double* parts, int count
   return block_reduce(s, red);
 }
 
+// Adaptive step-size rule with accept / reject, executed by ONE thread per attempt
+// (adaptive_step_size_strategy.cu:92-188) plus the bookkeeping the reference does on the host in take_step
+// (pdlp.cu:1188-1222): buffer swap, running-average weight, iteration counters.
+__device__ __forceinline__ void pdhg_step_rule(pdhg_ctl_t* ctl, double interaction, double dx2, double dy2)
+{
+  pdhg_ctl_t s     = *ctl;
+  s.interaction    = interaction;
+  s.norm_dx2       = dx2;
+  s.norm_dy2       = dy2;
+  s.attempts += 1;
+  const double pw       = s.primal_weight;
+  const double movement = s.primal_smoothing * pw * dx2 + (s.dual_smoothing / pw) * dy2;
+  bool accept;
+  if (movement <= 0.0 || movement >= 1.0e100) {
+    // numerical error (or exact convergence): the reference leaves the retry loop, still averages and
+    // swaps, and lets the next major iteration decide (pdlp.cu:1193-1221, :780-789)
+    s.valid = -1;
+    accept  = true;
+  } else {
+    const double inter = fabs(interaction);
+    s.k_pdhg += 1;
+    const double kc    = (double)s.k_pdhg;
+    const double limit = inter > 0.0 ? movement / inter : CUDART_INF;
+    accept             = s.step_size <= limit;
+    s.valid            = accept ? 1 : 0;
+    const double c1    = (1.0 - pow(kc + 1.0, -s.reduction_exponent)) * limit;
+    const double c2    = (1.0 + pow(kc + 1.0, -s.growth_exponent)) * s.step_size;
+    s.step_size        = fmin(c1, c2);
+    s.tau              = s.step_size / pw;
+    s.sigma            = s.step_size * pw;
+  }
+  if (accept) {
+    s.parity ^= 1;
+    s.pending_avg    = 1;
+    s.pending_weight = s.step_size;  // the already-updated step size (pdlp.cu:1216-1219)
+    s.sum_weights += s.step_size;
+    s.accepted += 1;
+    s.its_since_restart += 1;
+  } else {
+    s.pending_avg = 0;
+  }
+  s.active    = (s.valid != -1 && s.accepted < s.target) ? 1 : 0;
+  s.ticket[0] = 0u;
+  *ctl        = s;
+}
+
 // =============================================================================================
 // K1 — primal step.  x' = clamp(x - tau (c - A^T y), l, u), xbar = 2x' - x
 // (pdhg.cu:137-158 + utils.cuh:81-95), fused with the primal half of the running-average update
@@ -233,45 +279,75 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_step(
   const double dy2         = gather_partials(part_dy2, n_part_dy2, red);
   if (threadIdx.x != 0) return;
 
-  pdhg_ctl_t s     = *ctl;
-  s.interaction    = interaction;
-  s.norm_dx2       = dx2;
-  s.norm_dy2       = dy2;
-  s.attempts += 1;
-  const double pw       = s.primal_weight;
-  const double movement = s.primal_smoothing * pw * dx2 + (s.dual_smoothing / pw) * dy2;
-  bool accept;
-  if (movement <= 0.0 || movement >= 1.0e100) {
-    // numerical error (or exact convergence): the reference leaves the retry loop, still averages and
-    // swaps, and lets the next major iteration decide (pdlp.cu:1193-1221, :780-789)
-    s.valid = -1;
-    accept  = true;
-  } else {
-    const double inter = fabs(interaction);
-    s.k_pdhg += 1;
-    const double kc    = (double)s.k_pdhg;
-    const double limit = inter > 0.0 ? movement / inter : CUDART_INF;
-    accept             = s.step_size <= limit;
-    s.valid            = accept ? 1 : 0;
-    const double c1    = (1.0 - pow(kc + 1.0, -s.reduction_exponent)) * limit;
-    const double c2    = (1.0 + pow(kc + 1.0, -s.growth_exponent)) * s.step_size;
-    s.step_size        = fmin(c1, c2);
-    s.tau              = s.step_size / pw;
-    s.sigma            = s.step_size * pw;
+  pdhg_step_rule(ctl, interaction, dx2, dy2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-sharded (multi-GPU) variants of K3.  Each rank owns a block of rows of A; A_g^T y'_g is a PARTIAL
+// A^T y' that is summed over ranks (NCCL all-reduce on the solver stream) between K3a and K3b.  The extra slot
+// buf[n] carries this rank's ||dy||^2 through the same collective.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_partial(const pdhg_ctl_t* __restrict__ ctl,
+                                                                                   csr_warp_view_t AT,
+                                                                                   const double* __restrict__ ybuf0,
+                                                                                   const double* __restrict__ ybuf1,
+                                                                                   double* __restrict__ buf)
+{
+  if (!ctl->active) return;
+  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
+  const double* yn = ctl->parity ? ybuf0 : ybuf1;
+  struct payload_t {};
+  auto pre_op = [&](int) { return payload_t{}; };
+  auto row_op = [&](int j, double s, const payload_t&) { buf[j] = s; };
+  spmv_warp_rows<payload_t>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op);
+}
+// buf[slot] = sum of `count` per-CTA partials (one CTA, fixed order)
+__global__ void __launch_bounds__(EW_THREADS) k_sum_partials(const pdhg_ctl_t* __restrict__ ctl,
+                                                             const double* __restrict__ parts,
+                                                             int count,
+                                                             int n_quantities,
+                                                             double* __restrict__ out)
+{
+  if (ctl && !ctl->active) return;
+  __shared__ double red[32];
+  for (int q = 0; q < n_quantities; ++q) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s += parts[q * count + i];
+    s = block_reduce(s, red);
+    if (threadIdx.x == 0) out[q] = s;
   }
-  if (accept) {
-    s.parity ^= 1;
-    s.pending_avg    = 1;
-    s.pending_weight = s.step_size;  // the already-updated step size (pdlp.cu:1216-1219)
-    s.sum_weights += s.step_size;
-    s.accepted += 1;
-    s.its_since_restart += 1;
-  } else {
-    s.pending_avg = 0;
+}
+// K3b: after the all-reduce buf = A^T y' (global) and buf[n] = ||dy||^2 (global)
+__global__ void __launch_bounds__(EW_THREADS) k_interaction_step(pdhg_ctl_t* __restrict__ ctl,
+                                                                 int n,
+                                                                 const double* __restrict__ buf,
+                                                                 const double* __restrict__ xbuf0,
+                                                                 const double* __restrict__ xbuf1,
+                                                                 double* __restrict__ aty0,
+                                                                 double* __restrict__ aty1,
+                                                                 double* __restrict__ parts)
+{
+  if (!ctl->active) return;
+  __shared__ double red[32];
+  const int cur     = ctl->parity;
+  const double* x   = cur ? xbuf1 : xbuf0;
+  const double* xn  = cur ? xbuf0 : xbuf1;
+  const double* aty = cur ? aty1 : aty0;
+  double* atyn      = cur ? aty0 : aty1;
+  double acc[2]     = {0.0, 0.0};
+  const int stride  = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double s = buf[j];
+    atyn[j]        = s;
+    const double d = xn[j] - x[j];
+    acc[0] += d * (s - aty[j]);
+    acc[1] += d * d;
   }
-  s.active    = (s.valid != -1 && s.accepted < s.target) ? 1 : 0;
-  s.ticket[0] = 0u;
-  *ctl        = s;
+  if (!publish_and_elect<2>(acc, parts, &ctl->ticket[0], red)) return;
+  const double interaction = gather_partials(parts, gridDim.x, red);
+  const double dx2         = gather_partials(parts + gridDim.x, gridDim.x, red);
+  if (threadIdx.x != 0) return;
+  pdhg_step_rule(ctl, interaction, dx2, __ldcg(buf + n));
 }
 
 // Applies a still-pending running-average update (end of a batch, before averages are formed).
@@ -324,6 +400,71 @@ __device__ __forceinline__ double bound_value_product(double value, double lower
   if (value > 0.0) bound = lower;
   else if (value < 0.0) bound = upper;
   return isfinite(bound) ? value * bound : 0.0;
+}
+
+// Per-column part of the evaluation, for the current (v = 0) and the average (v = 1) iterate; s[v] = (A^T y_v)_j.
+// acc layout: {||g - rc||^2, rc-part of the dual objective, c.x, ||x||^2} x {cur, avg}
+__device__ __forceinline__ void eval_column(int j, const double (&s)[2], double cj, double lo, double hi,
+                                            const double (&xv)[2], int reduced_cost_rule, double* __restrict__ rc_cur,
+                                            double* __restrict__ rc_avg, double (&acc)[8])
+{
+  double* rcs[2] = {rc_cur, rc_avg};
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const double g     = cj - s[v];
+    const double bound = g > 0.0 ? lo : hi;  // utils.cuh:196-202
+    double rc;
+    if (g == 0.0) rc = g;
+    else if (reduced_cost_rule ? (fabs(xv[v] - bound) <= fabs(xv[v])) : isfinite(bound)) rc = g;  // :222-239
+    else rc = 0.0;
+    rcs[v][j]      = rc;
+    const double r = g - rc;
+    acc[v] += r * r;
+    acc[2 + v] += bound_value_product(rc, lo, hi);
+    acc[4 + v] += xv[v] * cj;
+    acc[6 + v] += xv[v] * xv[v];
+  }
+}
+
+// Final scalars of the evaluation, run by the last CTA of the column pass (all its threads enter).
+// parts: 8 x gridDim.x column partials; parts_rows: 6 x n_parts_rows row partials
+// ({viol^2, y-part of the dual objective, ||y||^2} x {cur, avg}).
+__device__ __forceinline__ void eval_finalize(pdhg_ctl_t* ctl, const double* parts, const double* parts_rows,
+                                              int n_parts_rows, const eval_consts_t& k, eval_t* out, double* red)
+{
+  double tot[14];
+  for (int q = 0; q < 8; ++q) tot[q] = gather_partials(parts + q * gridDim.x, gridDim.x, red);
+  for (int q = 0; q < 6; ++q) tot[8 + q] = gather_partials(parts_rows + q * n_parts_rows, n_parts_rows, red);
+  if (threadIdx.x != 0) return;
+  const double pw = ctl->primal_weight;
+  for (int v = 0; v < 2; ++v) {
+    eval_t e;
+    e.l2_primal_residual = sqrt(tot[8 + v]);
+    e.l2_dual_residual   = sqrt(tot[v]);
+    double p             = tot[4 + v];
+    double dobj          = tot[8 + 2 + v] + tot[2 + v];
+    if (k.objective_scaling_factor != 1.0 || k.objective_offset != 0.0) {
+      p    = k.objective_scaling_factor * p + k.objective_offset;
+      dobj = k.objective_scaling_factor * dobj + k.objective_offset;
+    }
+    e.primal_objective   = p;
+    e.dual_objective     = dobj;
+    e.gap                = fabs(p - dobj);
+    e.abs_objective      = fabs(p) + fabs(dobj);
+    e.l2_primal_variable = sqrt(tot[6 + v]);
+    e.l2_dual_variable   = sqrt(tot[8 + 4 + v]);
+    // termination_strategy.cu:117-250 (l2 criteria)
+    const bool gap_ok    = e.gap <= k.abs_gap_tol + k.rel_gap_tol * e.abs_objective;
+    const bool primal_ok = e.l2_primal_residual <= k.abs_primal_tol + k.rel_primal_tol * k.l2_norm_b;
+    const bool dual_ok   = e.l2_dual_residual <= k.abs_dual_tol + k.rel_dual_tol * k.l2_norm_c;
+    e.status             = (dual_ok && primal_ok && gap_ok) ? 1 : (primal_ok ? 7 : 6);
+    // pdlp_restart_strategy.cu:367-380
+    const double w2 = pw * pw;
+    e.kkt = sqrt(w2 * e.l2_primal_residual * e.l2_primal_residual + e.l2_dual_residual * e.l2_dual_residual / w2 +
+                 e.gap * e.gap);
+    e.pad  = 0;
+    out[v] = e;
+  }
 }
 
 // T1: rows of A.  parts layout: 6 x gridDim.x = {viol^2, y-part of dual objective, ||y||^2} x {cur, avg}
@@ -393,62 +534,44 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_eval_cols(pdhg_ctl_t* __restri
   };
   auto pre_op = [&](int j) { return payload_t{c[j], l[j], u[j], x_cur[j], x_avg[j]}; };
   auto row_op = [&](int j, const double (&s)[2], const payload_t& p) {
-    const double cj = p.c, lo = p.lo, hi = p.hi;
     const double xv[2] = {p.x0, p.x1};
-    double* rcs[2]     = {rc_cur, rc_avg};
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const double g     = cj - s[v];
-      const double bound = g > 0.0 ? lo : hi;  // utils.cuh:196-202
-      double rc;
-      if (g == 0.0) rc = g;
-      else if (k.reduced_cost_rule ? (fabs(xv[v] - bound) <= fabs(xv[v])) : isfinite(bound)) rc = g;  // :222-239
-      else rc = 0.0;
-      rcs[v][j]      = rc;
-      const double r = g - rc;
-      acc[v] += r * r;
-      acc[2 + v] += bound_value_product(rc, lo, hi);
-      acc[4 + v] += xv[v] * cj;
-      acc[6 + v] += xv[v] * xv[v];
-    }
+    eval_column(j, s, p.c, p.lo, p.hi, xv, k.reduced_cost_rule, rc_cur, rc_avg, acc);
   };
   const double* ys[2] = {y_cur, y_avg};
   spmv_pipeline<2, EVAL_STAGES, payload_t>(AT, ys, sm, pre_op, row_op);
 
   if (!publish_and_elect<8>(acc, parts, &ctl->ticket[1], red)) return;
-  double tot[14];
-  for (int q = 0; q < 8; ++q) tot[q] = gather_partials(parts + q * gridDim.x, gridDim.x, red);
-  for (int q = 0; q < 6; ++q) tot[8 + q] = gather_partials(parts_rows + q * n_parts_rows, n_parts_rows, red);
-  if (threadIdx.x != 0) return;
-  const double pw = ctl->primal_weight;
-  for (int v = 0; v < 2; ++v) {
-    eval_t e;
-    e.l2_primal_residual = sqrt(tot[8 + v]);
-    e.l2_dual_residual   = sqrt(tot[v]);
-    double p             = tot[4 + v];
-    double dobj          = tot[8 + 2 + v] + tot[2 + v];
-    if (k.objective_scaling_factor != 1.0 || k.objective_offset != 0.0) {
-      p    = k.objective_scaling_factor * p + k.objective_offset;
-      dobj = k.objective_scaling_factor * dobj + k.objective_offset;
-    }
-    e.primal_objective   = p;
-    e.dual_objective     = dobj;
-    e.gap                = fabs(p - dobj);
-    e.abs_objective      = fabs(p) + fabs(dobj);
-    e.l2_primal_variable = sqrt(tot[6 + v]);
-    e.l2_dual_variable   = sqrt(tot[8 + 4 + v]);
-    // termination_strategy.cu:117-250 (l2 criteria)
-    const bool gap_ok    = e.gap <= k.abs_gap_tol + k.rel_gap_tol * e.abs_objective;
-    const bool primal_ok = e.l2_primal_residual <= k.abs_primal_tol + k.rel_primal_tol * k.l2_norm_b;
-    const bool dual_ok   = e.l2_dual_residual <= k.abs_dual_tol + k.rel_dual_tol * k.l2_norm_c;
-    e.status             = (dual_ok && primal_ok && gap_ok) ? 1 : (primal_ok ? 7 : 6);
-    // pdlp_restart_strategy.cu:367-380
-    const double w2 = pw * pw;
-    e.kkt = sqrt(w2 * e.l2_primal_residual * e.l2_primal_residual + e.l2_dual_residual * e.l2_dual_residual / w2 +
-                 e.gap * e.gap);
-    e.pad  = 0;
-    out[v] = e;
+  eval_finalize(ctl, parts, parts_rows, n_parts_rows, k, out, red);
+}
+
+// Row-sharded mode: A^T y (current, average) arrives all-reduced in aty_cur / aty_avg; same column math, element-wise.
+__global__ void __launch_bounds__(EW_THREADS) k_eval_cols_from_aty(pdhg_ctl_t* __restrict__ ctl,
+                                                                   int n,
+                                                                   const double* __restrict__ aty_cur,
+                                                                   const double* __restrict__ aty_avg,
+                                                                   const double* __restrict__ x_cur,
+                                                                   const double* __restrict__ x_avg,
+                                                                   const double* __restrict__ c,
+                                                                   const double* __restrict__ l,
+                                                                   const double* __restrict__ u,
+                                                                   double* __restrict__ rc_cur,
+                                                                   double* __restrict__ rc_avg,
+                                                                   double* __restrict__ parts,
+                                                                   const double* __restrict__ parts_rows,
+                                                                   int n_parts_rows,
+                                                                   eval_consts_t k,
+                                                                   eval_t* __restrict__ out)
+{
+  __shared__ double red[32];
+  double acc[8]    = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double s[2]  = {aty_cur[j], aty_avg[j]};
+    const double xv[2] = {x_cur[j], x_avg[j]};
+    eval_column(j, s, c[j], l[j], u[j], xv, k.reduced_cost_rule, rc_cur, rc_avg, acc);
   }
+  if (!publish_and_elect<8>(acc, parts, &ctl->ticket[1], red)) return;
+  eval_finalize(ctl, parts, parts_rows, n_parts_rows, k, out, red);
 }
 
 // Averages + in-place unscaling ahead of the evaluation (pdlp.cu:1103-1136,
@@ -483,9 +606,27 @@ __global__ void __launch_bounds__(EW_THREADS) k_scale_back(int n, double* __rest
   }
 }
 
-// Squared distance of the restart candidate to the last restart point for primal and dual, then the
-// primal-weight update (pdlp_restart_strategy.cu:685-732, 753-801, 1681-1714).  Single CTA is enough
-// off the hot path?  No: n can be 10M, so grid-wide with an elected finisher.
+// Primal-weight update from the squared distances to the last restart point (pdlp_restart_strategy.cu:685-732).
+__device__ __forceinline__ void update_primal_weight(pdhg_ctl_t* ctl, double dp2, double dd2, double smoothing)
+{
+  const double pd = sqrt(dp2), dd = sqrt(dd2);
+  const double guard = 1.0e-10;
+  if (pd < guard || pd >= 1.0 / guard || dd < guard || dd >= 1.0 / guard) return;
+  const double lw    = smoothing * log(dd / pd) + (1.0 - smoothing) * log(ctl->primal_weight);
+  const double pw    = exp(lw);
+  ctl->primal_weight = pw;
+  ctl->tau           = ctl->step_size / pw;
+  ctl->sigma         = ctl->step_size * pw;
+}
+// row-sharded mode: distances[0] = primal (replicated), distances[1] = dual (all-reduced)
+__global__ void k_update_primal_weight(pdhg_ctl_t* ctl, const double* distances, double smoothing)
+{
+  update_primal_weight(ctl, distances[0], distances[1], smoothing);
+}
+
+// Squared distance of the restart candidate to the last restart point for primal and dual
+// (pdlp_restart_strategy.cu:753-801, 1681-1714: plain L2), then the primal-weight update, or — when `distances_out`
+// is given (row-sharded mode, the dual part still has to be summed over ranks) — just the two sums.
 __global__ void __launch_bounds__(EW_THREADS) k_restart_distance_and_weight(pdhg_ctl_t* __restrict__ ctl,
                                                                             int n,
                                                                             const double* __restrict__ cand_x,
@@ -494,7 +635,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_restart_distance_and_weight(pdhg
                                                                             const double* __restrict__ cand_y,
                                                                             const double* __restrict__ last_y,
                                                                             double smoothing,
-                                                                            double* __restrict__ parts)
+                                                                            double* __restrict__ parts,
+                                                                            double* __restrict__ distances_out)
 {
   __shared__ double red[32];
   double acc[2]    = {0.0, 0.0};
@@ -511,14 +653,12 @@ __global__ void __launch_bounds__(EW_THREADS) k_restart_distance_and_weight(pdhg
   const double dp2 = gather_partials(parts, gridDim.x, red);
   const double dd2 = gather_partials(parts + gridDim.x, gridDim.x, red);
   if (threadIdx.x != 0) return;
-  const double pd = sqrt(dp2), dd = sqrt(dd2);
-  const double guard = 1.0e-10;
-  if (pd < guard || pd >= 1.0 / guard || dd < guard || dd >= 1.0 / guard) return;
-  const double lw    = smoothing * log(dd / pd) + (1.0 - smoothing) * log(ctl->primal_weight);
-  const double pw    = exp(lw);
-  ctl->primal_weight = pw;
-  ctl->tau           = ctl->step_size / pw;
-  ctl->sigma         = ctl->step_size * pw;
+  if (distances_out) {
+    distances_out[0] = dp2;
+    distances_out[1] = dd2;
+    return;
+  }
+  update_primal_weight(ctl, dp2, dd2, smoothing);
 }
 __global__ void k_reset_after_restart(pdhg_ctl_t* ctl)
 {

@@ -14,6 +14,7 @@
 // running sums; averages; last-restart point; reduced costs; bound / cost vectors (scaled + unscaled).
 #include "pdlp_solver.hpp"
 
+#include "dist_comm.hpp"
 #include "pdlp_kernels.cuh"
 
 #include <math_constants.h>
@@ -95,6 +96,17 @@ std::vector<int2> build_warp_blocks(const std::vector<int>& off)
   return wd;
 }
 
+// Row-block / warp-block schedules from HOST row offsets.
+void upload_schedules(csr_dev_t& d, const std::vector<int>& off, cudaStream_t s)
+{
+  auto blocks = build_row_blocks(off);
+  d.n_blocks  = (int)blocks.size();
+  d.blk.upload(blocks, s);
+  auto wblocks = build_warp_blocks(off);
+  d.n_wb       = (int)wblocks.size() - 1;
+  d.wdesc.upload(wblocks, s);
+}
+
 void upload_csr(csr_dev_t& d, int rows, int cols, const std::vector<int>& off, const std::vector<int>& idx,
                 const std::vector<double>& val, cudaStream_t s)
 {
@@ -104,34 +116,32 @@ void upload_csr(csr_dev_t& d, int rows, int cols, const std::vector<int>& off, c
   d.off.upload(off, s, SPMV_TAIL_SLACK);
   d.idx.upload(idx, s, SPMV_TAIL_SLACK);
   d.val.upload(val, s, SPMV_TAIL_SLACK);
-  auto blocks = build_row_blocks(off);
-  d.n_blocks  = (int)blocks.size();
-  d.blk.upload(blocks, s);
-  auto wblocks = build_warp_blocks(off);
-  d.n_wb       = (int)wblocks.size() - 1;
-  d.wdesc.upload(wblocks, s);
+  upload_schedules(d, off, s);
 }
 
-// Stable CSR transpose on the host (row indices ascending inside each transposed row — the order
-// cusparseCsr2cscEx2 gives the reference, mip/problem/problem.cu:277-309).
-void transpose_host(int rows, int cols, const std::vector<int>& off, const std::vector<int>& idx,
-                    const std::vector<double>& val, std::vector<int>& toff, std::vector<int>& tidx,
-                    std::vector<double>& tval)
+}  // namespace
+
+void csr_transpose_device(int rows, int cols, int nnz, const int* off, const int* idx, const double* val, int* toff,
+                          int* tidx, double* tval, cudaStream_t stream);  // csr_transpose.cu
+
+namespace {
+
+// A^T on the device (stable order, see csr_transpose.cu); only its row offsets come back to the host, to cut the schedules.
+void transpose_to(csr_dev_t& t, const csr_dev_t& a, cudaStream_t s)
 {
-  toff.assign(cols + 1, 0);
-  tidx.resize(idx.size());
-  tval.resize(val.size());
-  for (int j : idx) toff[j + 1]++;
-  for (int j = 0; j < cols; ++j) toff[j + 1] += toff[j];
-  std::vector<int> cur(toff.begin(), toff.end() - 1);
-  for (int i = 0; i < rows; ++i)
-    for (int p = off[i]; p < off[i + 1]; ++p) {
-      const int q = cur[idx[p]]++;
-      tidx[q]     = i;
-      tval[q]     = val[p];
-    }
+  t.rows = a.cols;
+  t.cols = a.rows;
+  t.nnz  = a.nnz;
+  t.off.resize((size_t)t.rows + 1, SPMV_TAIL_SLACK);
+  t.idx.resize(t.nnz, SPMV_TAIL_SLACK);
+  t.val.resize(t.nnz, SPMV_TAIL_SLACK);
+  csr_transpose_device(a.rows, a.cols, a.nnz, a.off.data(), a.idx.data(), a.val.data(), t.off.data(), t.idx.data(),
+                       t.val.data(), s);
+  std::vector<int> toff((size_t)t.rows + 1);
+  t.off.download(toff.data(), s);
+  CUOPT_CUDA_TRY(cudaStreamSynchronize(s));
+  upload_schedules(t, toff, s);
 }
-
 
 constexpr size_t SMEM_EVAL = sizeof(spmv_smem_t<2, EVAL_STAGES>);
 
@@ -158,6 +168,9 @@ struct pdlp_solver_t::impl_t {
   dvec<double> c, l, u, lc, uc, cs, ls, us, lcs, ucs, Dr, Dc;
   dvec<double> xbuf[2], ybuf[2], atybuf[2], xbar, sum_x, sum_y, x_avg, y_avg, x_lr, y_lr, rc_cur, rc_avg;
   dvec<double> part_dy2, part_k3, part_rows, part_cols, part_misc, scratch_n, scratch_m, d_scalar;
+  dvec<double> dist_buf;  // row-sharded mode: partial A^T y' (+1 slot) / 2n for the evaluation, all-reduced in place
+  const dist_context_t* dist = nullptr;
+  bool sharded() const { return dist != nullptr && dist->world > 1; }
   dvec<unsigned> d_ticket;
   dvec<pdhg_ctl_t> d_ctl;
   dvec<eval_t> d_eval;
@@ -236,11 +249,8 @@ struct pdlp_solver_t::impl_t {
     for (int i = 0; i < m; ++i)
       if (hlc[i] > huc[i]) throw lp_error(error_type_t::ValidationError, "Constraint lower bound above upper bound");
 
-    std::vector<int> toff, tidx;
-    std::vector<double> tval;
-    transpose_host(m, n, p.A_offsets, p.A_indices, p.A_values, toff, tidx, tval);
     upload_csr(A, m, n, p.A_offsets, p.A_indices, p.A_values, stream);
-    upload_csr(AT, n, m, toff, tidx, tval, stream);
+    transpose_to(AT, A, stream);
     As.alias_structure_copy_values(A, stream);
     ATs.alias_structure_copy_values(AT, stream);
     c.upload(hc, stream); l.upload(hl, stream); u.upload(hu, stream); lc.upload(hlc, stream); uc.upload(huc, stream);
@@ -281,8 +291,9 @@ struct pdlp_solver_t::impl_t {
     part_dy2.resize(grid_k2);
     part_k3.resize(2 * (size_t)grid_k3);
     part_rows.resize(6 * (size_t)grid_er);
-    part_cols.resize(8 * (size_t)grid_ec);
+    part_cols.resize(8 * (size_t)std::max(grid_ec, grid_n));
     part_misc.resize(2 * (size_t)std::max(grid_misc, ew_grid(nnz, sms)));
+    if (sharded()) { dist_buf.resize(2 * (size_t)n + 8); dist_buf.zero(stream); use_graphs = false; }
     d_scalar.resize(8);
     d_ticket.resize(4);
     d_ticket.zero(stream);
@@ -294,11 +305,13 @@ struct pdlp_solver_t::impl_t {
   }
 
   // deterministic setup reduction, result on the host
-  double setup_reduce(int kind, int count, const double* a, const double* b, double weight)
+  // `across_ranks`: the reduced quantity lives on row-sharded data (rows of A, lc/uc), combine over ranks too
+  double setup_reduce(int kind, int count, const double* a, const double* b, double weight, bool across_ranks = false)
   {
     const int g = ew_grid(count, sms);
     k_setup_reduce<<<g, EW_THREADS, 0, stream>>>(kind, count, a, b, weight, part_misc.data(), d_ticket.data(), d_scalar.data());
     check_launch();
+    if (across_ranks && sharded()) dist->allreduce(d_scalar.data(), 1, kind == 0, stream);
     CUOPT_CUDA_TRY(cudaMemcpyAsync(h_scalar, d_scalar.data(), sizeof(double), cudaMemcpyDeviceToHost, stream));
     sync();
     return h_scalar[0];
@@ -317,6 +330,8 @@ struct pdlp_solver_t::impl_t {
                                                    mode, pr, scratch_m.data());
       k_row_scaling_stat<<<wg_n, 256, 0, stream>>>(n, AT.off.data(), AT.idx.data(), AT.val.data(), Dc.data(), Dr.data(),
                                                    1, mode, pc, scratch_n.data());
+      // row-sharded: a column's statistic spans the row blocks of all ranks (max for Ruiz, sum for Pock-Chambolle)
+      if (sharded()) dist->allreduce(scratch_n.data(), n, mode == 0, stream);
       k_apply_scaling_stat<<<grid_m, EW_THREADS, 0, stream>>>(m, Dr.data(), scratch_m.data());
       k_apply_scaling_stat<<<grid_n, EW_THREADS, 0, stream>>>(n, Dc.data(), scratch_n.data());
     };
@@ -348,12 +363,12 @@ struct pdlp_solver_t::impl_t {
 
   double initial_step_size(const csr_dev_t& M)  // pdlp.cu:1225-1258
   {
-    const double mx = setup_reduce(0, M.nnz, M.val.data(), nullptr, 0.0);
+    const double mx = setup_reduce(0, M.nnz, M.val.data(), nullptr, 0.0, true);
     return mx == 0.0 ? 0.0 : hp.initial_step_size_scaling / mx;
   }
   double initial_primal_weight(const dvec<double>& cc, const dvec<double>& lo, const dvec<double>& hi)  // pdlp.cu:1261-1309
   {
-    const double bn = std::sqrt(setup_reduce(2, m, lo.data(), hi.data(), hp.initial_primal_weight_b_scaling));
+    const double bn = std::sqrt(setup_reduce(2, m, lo.data(), hi.data(), hp.initial_primal_weight_b_scaling, true));
     const double cn = std::sqrt(setup_reduce(1, n, cc.data(), nullptr, hp.initial_primal_weight_c_scaling));
     return (bn > 0.0 && cn > 0.0) ? hp.primal_importance * (cn / bn) : hp.primal_importance;
   }
@@ -364,7 +379,7 @@ struct pdlp_solver_t::impl_t {
     const double t0 = now_seconds();
     // norms of the unscaled problem used by the relative tolerances (convergence_information.cu:74-82)
     l2_norm_c = std::sqrt(setup_reduce(1, n, c.data(), nullptr, 1.0));
-    l2_norm_b = std::sqrt(setup_reduce(2, m, lc.data(), uc.data(), 1.0));
+    l2_norm_b = std::sqrt(setup_reduce(2, m, lc.data(), uc.data(), 1.0, true));
     compute_scaling_vectors();
     double step = 0.0, weight = 0.0;
     if (hp.compute_initial_step_size_before_scaling) step = initial_step_size(A);
@@ -404,15 +419,25 @@ struct pdlp_solver_t::impl_t {
                                                       xbar.data());
     k_dual_step<<<grid_k2, WARP_THREADS, 0, stream>>>(d_ctl.data(), As.warp_view(), xbar.data(), ybuf[0].data(), ybuf[1].data(),
                                                       lcs.data(), ucs.data(), sum_y.data(), part_dy2.data());
-    k_transpose_step<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
-                                                           xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
-                                                           atybuf[1].data(), part_k3.data(), part_dy2.data(), grid_k2);
+    if (!sharded()) {
+      k_transpose_step<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
+                                                             xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
+                                                             atybuf[1].data(), part_k3.data(), part_dy2.data(), grid_k2);
+      return;
+    }
+    // row-sharded: partial A_g^T y'_g and this rank's ||dy||^2 -> one all-reduce of n + 1 doubles -> K3b
+    k_transpose_partial<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
+                                                              dist_buf.data());
+    k_sum_partials<<<1, EW_THREADS, 0, stream>>>(d_ctl.data(), part_dy2.data(), grid_k2, 1, dist_buf.data() + n);
+    dist->allreduce(dist_buf.data(), (size_t)n + 1, false, stream);
+    k_interaction_step<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, dist_buf.data(), xbuf[0].data(), xbuf[1].data(),
+                                                          atybuf[0].data(), atybuf[1].data(), part_k3.data());
   }
 
   void launch_attempts(int count)
   {
     if (count <= 0) return;
-    launches += 3LL * count;
+    launches += (sharded() ? 5LL : 3LL) * count;
     if (!use_graphs || count == 1) {
       for (int i = 0; i < count; ++i) enqueue_attempt();
       check_launch();
@@ -446,6 +471,7 @@ struct pdlp_solver_t::impl_t {
     if (need_aty) {  // pdhg.cu:183-202
       const int cur = h_ctl->parity;
       k_spmv<<<grid_sp, WARP_THREADS, 0, stream>>>(ATs.warp_view(), ybuf[cur].data(), atybuf[cur].data());
+      if (sharded()) dist->allreduce(atybuf[cur].data(), n, false, stream);
       ++launches;
       need_aty = false;
     }
@@ -500,10 +526,24 @@ struct pdlp_solver_t::impl_t {
                                                              y_avg.data(), Dr.data());
     k_eval_rows<<<grid_er, SPMV_THREADS, SMEM_EVAL, stream>>>(A.view(), xbuf[cur].data(), x_avg.data(), ybuf[cur].data(),
                                                       y_avg.data(), lc.data(), uc.data(), part_rows.data());
-    k_eval_cols<<<grid_ec, SPMV_THREADS, SMEM_EVAL, stream>>>(d_ctl.data(), AT.view(), xbuf[cur].data(), x_avg.data(),
-                                                      ybuf[cur].data(), y_avg.data(), c.data(), l.data(), u.data(),
-                                                      rc_cur.data(), rc_avg.data(), part_cols.data(), part_rows.data(),
-                                                      grid_er, eval_consts(), d_eval.data());
+    if (!sharded()) {
+      k_eval_cols<<<grid_ec, SPMV_THREADS, SMEM_EVAL, stream>>>(d_ctl.data(), AT.view(), xbuf[cur].data(), x_avg.data(),
+                                                        ybuf[cur].data(), y_avg.data(), c.data(), l.data(), u.data(),
+                                                        rc_cur.data(), rc_avg.data(), part_cols.data(), part_rows.data(),
+                                                        grid_er, eval_consts(), d_eval.data());
+    } else {
+      // row-sharded: the six row sums and both A^T y products are partial; combine over ranks, then the column pass
+      k_sum_partials<<<1, EW_THREADS, 0, stream>>>(nullptr, part_rows.data(), grid_er, 6, d_scalar.data());
+      dist->allreduce(d_scalar.data(), 6, false, stream);
+      k_spmv<<<grid_sp, WARP_THREADS, 0, stream>>>(AT.warp_view(), ybuf[cur].data(), dist_buf.data());
+      k_spmv<<<grid_sp, WARP_THREADS, 0, stream>>>(AT.warp_view(), y_avg.data(), dist_buf.data() + n);
+      dist->allreduce(dist_buf.data(), 2 * (size_t)n, false, stream);
+      k_eval_cols_from_aty<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, dist_buf.data(), dist_buf.data() + n,
+                                                              xbuf[cur].data(), x_avg.data(), c.data(), l.data(), u.data(),
+                                                              rc_cur.data(), rc_avg.data(), part_cols.data(),
+                                                              d_scalar.data(), 1, eval_consts(), d_eval.data());
+      launches += 3;
+    }
     launches += 4;
     check_launch();
     CUOPT_CUDA_TRY(cudaMemcpyAsync(h_eval, d_eval.data(), 2 * sizeof(eval_t), cudaMemcpyDeviceToHost, stream));
@@ -543,7 +583,16 @@ struct pdlp_solver_t::impl_t {
 
   bool check_limits()  // pdlp.cu:265-331
   {
-    if (now_seconds() - t_start >= st.time_limit) {
+    bool out_of_time = now_seconds() - t_start >= st.time_limit;
+    if (sharded() && std::isfinite(st.time_limit)) {  // every rank must take the same branch: any rank over => all stop
+      h_scalar[1] = out_of_time ? 1.0 : 0.0;
+      CUOPT_CUDA_TRY(cudaMemcpyAsync(d_scalar.data() + 7, h_scalar + 1, sizeof(double), cudaMemcpyHostToDevice, stream));
+      dist->allreduce(d_scalar.data() + 7, 1, true, stream);
+      CUOPT_CUDA_TRY(cudaMemcpyAsync(h_scalar + 1, d_scalar.data() + 7, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      sync();
+      out_of_time = h_scalar[1] > 0.5;
+    }
+    if (out_of_time) {
       fill_solution(false, termination_status_t::TimeLimit);
       return true;
     }
@@ -614,7 +663,11 @@ struct pdlp_solver_t::impl_t {
       dvec<double>& cy   = use_avg ? y_avg : ybuf[cur];
       k_restart_distance_and_weight<<<grid_misc, EW_THREADS, 0, stream>>>(
         d_ctl.data(), n, cx.data(), x_lr.data(), m, cy.data(), y_lr.data(), hp.primal_weight_update_smoothing,
-        part_misc.data());
+        part_misc.data(), sharded() ? d_scalar.data() : nullptr);
+      if (sharded()) {  // the dual distance is a sum over the row blocks of all ranks; the primal one is replicated
+        dist->allreduce(d_scalar.data() + 1, 1, false, stream);
+        k_update_primal_weight<<<1, 1, 0, stream>>>(d_ctl.data(), d_scalar.data(), hp.primal_weight_update_smoothing);
+      }
       if (use_avg) {
         xbuf[cur].copy_from(x_avg, stream);
         ybuf[cur].copy_from(y_avg, stream);
@@ -707,10 +760,11 @@ struct pdlp_solver_t::impl_t {
 };
 
 // ------------------------------------------------------------------------------------------------
-pdlp_solver_t::pdlp_solver_t(const lp_problem_t& problem, const pdlp_settings_t& settings, dist_context_t*)
+pdlp_solver_t::pdlp_solver_t(const lp_problem_t& problem, const pdlp_settings_t& settings, dist_context_t* dist)
   : impl_(new impl_t)
 {
   const double t0 = now_seconds();
+  impl_->dist = dist;
   impl_->build(problem, settings);
   impl_->sol.stats.setup_seconds += now_seconds() - t0;
 }
@@ -850,11 +904,11 @@ kernel_profile_t pdlp_solver_t::profile_kernels(int warmup_steps, int reps)
   return out;
 }
 
-lp_solution_t solve_lp(const lp_problem_t& problem, const pdlp_settings_t& settings)
+lp_solution_t solve_lp(const lp_problem_t& problem, const pdlp_settings_t& settings, dist_context_t* dist)
 {
   lp_solution_t sol;
   try {
-    pdlp_solver_t solver(problem, settings);
+    pdlp_solver_t solver(problem, settings, dist);
     sol = solver.run();
   } catch (const lp_error& e) {
     if (e.type == error_type_t::Success) {  // "cannot run" cases the reference answers with a NumericalError solution

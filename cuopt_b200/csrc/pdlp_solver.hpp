@@ -48,6 +48,7 @@ class pdlp_solver_t {
 };
 
 // solve_lp for method == PDLP (and what Concurrent / DualSimplex fall back to in this build).
-lp_solution_t solve_lp(const lp_problem_t& problem, const pdlp_settings_t& settings);
+// `dist` != nullptr: `problem` holds THIS RANK'S block of rows (all columns); collective over the communicator.
+lp_solution_t solve_lp(const lp_problem_t& problem, const pdlp_settings_t& settings, dist_context_t* dist = nullptr);
 
 }  // namespace cuopt_b200

@@ -1,0 +1,69 @@
+"""Host-side helpers for the row-sharded multi-GPU solve (one process per GPU, torch.distributed for the plumbing).
+
+shard_rows      contiguous, nnz-balanced partition of the constraint rows (the unit the path shards on)
+local_problem   the rows of one rank as a C-ABI problem (all columns, global column indices)
+bootstrap       NCCL communicator of libcuopt.so: rank 0 creates the unique id, torch.distributed broadcasts it
+reference_protocol_step   numpy restatement of what ONE distributed PDHG attempt exchanges (used by the gloo CPU tests)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(offsets: np.ndarray, world: int) -> np.ndarray:
+    """Row boundaries b[0..world]: rank g owns rows [b[g], b[g+1]).  Balanced on nnz + rows (both cost memory traffic)."""
+    m = len(offsets) - 1
+    cost = offsets.astype(np.int64) + np.arange(m + 1, dtype=np.int64)  # cumulative (nnz + rows)
+    targets = cost[-1] * np.arange(1, world, dtype=np.float64) / world
+    cuts = np.searchsorted(cost, targets, side="left")
+    b = np.concatenate([[0], cuts, [m]]).astype(np.int64)
+    return np.maximum.accumulate(b)
+
+
+def shard_rows(lp, rank: int, world: int):
+    """(row_start, row_end, local CSR offsets, indices, values, con_lb, con_ub) of `rank`."""
+    b = shard_bounds(lp.offsets, world)
+    r0, r1 = int(b[rank]), int(b[rank + 1])
+    lo, hi = int(lp.offsets[r0]), int(lp.offsets[r1])
+    off = (lp.offsets[r0:r1 + 1] - lo).astype(np.int32)
+    return r0, r1, off, lp.indices[lo:hi], lp.values[lo:hi], lp.con_lb[r0:r1], lp.con_ub[r0:r1]
+
+
+def local_problem(lp, rank: int, world: int):
+    from . import capi
+    r0, r1, off, idx, val, clb, cub = shard_rows(lp, rank, world)
+    p = capi.Problem.create_ranged(off, idx, val, clb, cub, lp.c, lp.var_lb, lp.var_ub)
+    return p, (r0, r1)
+
+
+def bootstrap(rank: int, world: int, device=None):
+    """Create the libcuopt NCCL communicator; the 128-byte unique id travels through torch.distributed."""
+    import torch
+    import torch.distributed as dist
+
+    from . import capi
+    uid = capi.Dist.unique_id() if rank == 0 else bytes(128)
+    t = torch.frombuffer(bytearray(uid), dtype=torch.uint8).clone()
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=0)
+    return capi.Dist(rank, world, bytes(t.cpu().numpy().tobytes()))
+
+
+def reference_protocol_step(shard, x, x_next, aty, y_local, sigma, lc, uc, allreduce_sum):
+    """What one attempt exchanges in the row-sharded scheme, in numpy (float64), for the CPU protocol tests.
+
+    shard = (A_local as scipy.sparse.csr_matrix); vectors of length n are replicated, y / bounds are local rows.
+    Returns (y_next_local, aty_next (global, identical on all ranks), interaction, ||dx||^2, ||dy||^2).
+    One collective: the all-reduce of [A_g^T y'_g ; ||dy_g||^2]  (n + 1 doubles).
+    """
+    A = shard
+    xbar = x_next - x + x_next
+    ybar = y_local - sigma * (A @ xbar)
+    y_next = np.maximum(ybar + sigma * lc, np.minimum(ybar + sigma * uc, 0.0))
+    dy = y_next - y_local
+    buf = np.concatenate([A.T @ y_next, [float(dy @ dy)]])
+    buf = allreduce_sum(buf)
+    aty_next, dy2 = buf[:-1], float(buf[-1])
+    dx = x_next - x
+    return y_next, aty_next, float(dx @ (aty_next - aty)), float(dx @ dx), dy2

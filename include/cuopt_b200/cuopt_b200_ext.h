@@ -87,6 +87,22 @@ cuopt_int_t cuOptB200SolverProfileKernels(cuOptB200Solver solver,
                                           cuopt_int_t reps,
                                           cuOptB200KernelProfile* profile);
 
+/* ---- multi-GPU (one process per GPU, rows of A sharded over the ranks) ---------------------
+ * The reference cannot use several GPUs for one LP (docs/cuopt/source/faq.rst:53); this is new functionality.
+ * Bootstrap: rank 0 calls cuOptB200DistGetUniqueId and broadcasts the 128 bytes by any means (torch.distributed,
+ * MPI, a file); every rank then calls cuOptB200DistInit on its own CUDA device.
+ * cuOptB200SolveDistributed is collective: each rank passes a problem holding ITS contiguous block of constraint
+ * rows (all columns, global column indices; objective, variable bounds and types replicated).  Every rank gets the
+ * full primal solution and reduced costs; the dual solution returned is the rank's own block of rows. */
+typedef void* cuOptB200Dist;
+cuopt_int_t cuOptB200DistGetUniqueId(char* unique_id_128_bytes);
+cuopt_int_t cuOptB200DistInit(cuopt_int_t rank, cuopt_int_t world_size, const char* unique_id_128_bytes, cuOptB200Dist* dist_ptr);
+void cuOptB200DistDestroy(cuOptB200Dist* dist_ptr);
+cuopt_int_t cuOptB200SolveDistributed(cuOptOptimizationProblem local_rows_problem,
+                                      cuOptSolverSettings settings,
+                                      cuOptB200Dist dist,
+                                      cuOptSolution* solution_ptr);
+
 /* cuOptReadProblem with an explicit format switch (the reference C ABI always parses free format;
  * its C++ parse_mps(file, fixed_mps_format) has the flag: cpp/libmps_parser/include/mps_parser/parser.hpp:33). */
 cuopt_int_t cuOptB200ReadProblem(const char* filename, cuopt_int_t fixed_format, cuOptOptimizationProblem* problem_ptr);

@@ -1,0 +1,108 @@
+"""Host-side logic of the row-sharded (N > 1) path, on CPU with the gloo backend, world_size 2 and 3:
+  * the row partition tiles the matrix and balances nnz,
+  * the ONE collective an attempt needs (all-reduce of [A_g^T y'_g ; ||dy_g||^2]) reproduces the single-process
+    quantities of the oracle's attempt (A^T y', interaction, movement terms),
+  * every rank derives bit-identical scalars from the all-reduced buffer (=> identical accept/reject decisions).
+The CUDA side of the same protocol is exercised by tests/test_gpu_dist.py on >= 2 GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cuopt_b200 import dist as cdist
+from cuopt_b200 import lpgen
+from oracle import pdlp_oracle as po
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lp = lpgen.sparse_lp(3000, 2500, 6, seed=11)
+        # the oracle provides a realistic scaled state after a few iterations (same on every rank: deterministic)
+        o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub)
+        o.run(9)
+        x, y, aty = o.vector("x"), o.vector("y"), o.vector("aty")
+        tau, sigma = o.scalar("tau"), o.scalar("sigma")
+        want = o.single_attempt(x, y, aty, tau, sigma)
+        dr, dc = o.vector("row_scaling"), o.vector("col_scaling")
+        A = sp.csr_matrix((lp.values, lp.indices, lp.offsets), shape=(lp.m, lp.n))
+        As = sp.diags(dr) @ A @ sp.diags(dc)
+        lcs, ucs = o.vector("scaled_lc"), o.vector("scaled_uc")
+        b = cdist.shard_bounds(lp.offsets, world)
+        r0, r1 = int(b[rank]), int(b[rank + 1])
+
+        def allreduce_sum(buf):
+            t = torch.from_numpy(buf.copy())
+            dist.all_reduce(t)
+            return t.numpy()
+
+        y_next, aty_next, inter, dx2, dy2 = cdist.reference_protocol_step(
+            As[r0:r1].tocsr(), x, want["x_next"], aty, y[r0:r1], sigma, lcs[r0:r1], ucs[r0:r1], allreduce_sum)
+        ok = (np.allclose(y_next, want["y_next"][r0:r1], rtol=1e-12, atol=1e-13)
+              and np.allclose(aty_next, want["aty_next"], rtol=1e-11, atol=1e-12)
+              and abs(dx2 - want["norm_dx2"]) <= 1e-11 * want["norm_dx2"]
+              and abs(dy2 - want["norm_dy2"]) <= 1e-11 * want["norm_dy2"]
+              and abs(inter - want["interaction"]) <= 1e-9 * max(abs(want["interaction"]), want["norm_dx2"]))
+        # identical bits on every rank
+        g = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([inter, dx2, dy2], dtype=torch.float64))
+        same = all(torch.equal(g[0], t) for t in g)
+        q.put((rank, bool(ok), bool(same), r0, r1))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_attempt_protocol_matches_single_process(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(60)
+    assert all(r[1] for r in res), res
+    assert all(r[2] for r in res), res
+    # the shards tile [0, m)
+    assert res[0][3] == 0 and res[-1][4] == 3000 and all(res[i][4] == res[i + 1][3] for i in range(world - 1))
+
+
+def test_shard_bounds_balance_and_edge_cases():
+    lp = lpgen.sparse_lp(10_000, 8_000, 8, seed=3)
+    for world in (1, 2, 4, 8):
+        b = cdist.shard_bounds(lp.offsets, world)
+        assert b[0] == 0 and b[-1] == lp.m and np.all(np.diff(b) >= 0)
+        nnz = np.diff(lp.offsets[b])
+        assert nnz.max() <= 1.05 * lp.nnz / world + 8
+    # ragged: one dense row and many empty ones
+    off = np.array([0, 0, 0, 1000, 1000, 1001, 1001], np.int32)
+    b = cdist.shard_bounds(off, 3)
+    assert b[0] == 0 and b[-1] == 6 and np.all(np.diff(b) >= 0)
+    # more ranks than rows: some shards are empty
+    b = cdist.shard_bounds(np.array([0, 3, 5], np.int32), 4)
+    assert b[0] == 0 and b[-1] == 2 and np.all(np.diff(b) >= 0)
+
+
+def test_shards_reassemble_the_matrix():
+    lp = lpgen.sparse_lp(5000, 4000, 5, seed=9)
+    rows = []
+    for r in range(4):
+        r0, r1, off, idx, val, clb, cub = cdist.shard_rows(lp, r, 4)
+        rows.append(sp.csr_matrix((val, idx, off), shape=(r1 - r0, lp.n)))
+        assert np.array_equal(clb, lp.con_lb[r0:r1]) and np.array_equal(cub, lp.con_ub[r0:r1])
+    A = sp.csr_matrix((lp.values, lp.indices, lp.offsets), shape=(lp.m, lp.n))
+    assert (sp.vstack(rows) != A).nnz == 0
