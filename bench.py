@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""bench.py — PDLP iterations/sec on BASELINE.json's configs[1] (synthetic sparse LP, 1M x 1M, 8 nnz/row, fp64).
+"""bench.py — PDLP iterations/sec on BASELINE.json's headline workload: the synthetic sparse LP with 10M variables x
+10M constraints, 8 nnz/row, fp64 (configs[3]'s instance; it fits one B200, so every N = 1, 2, 4, 8 runs the SAME LP and
+the N-GPU numbers are strong scaling).  --workload c2 selects configs[1] (1M x 1M), --workload c3 the pds-shaped
+multicommodity LP of configs[2] (both single-GPU profile workloads).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (through the C ABI)
   python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference PDLP on host cores
@@ -74,18 +77,30 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+WORKLOADS = {"c4": (10_000_000, 10_000_000), "c2": (1_000_000, 1_000_000)}
+TRANSPORTS = {"p2p": "NVLink peer stores issued by the producing kernels (xbar slices, A_g^T y partials, 3 scalars); "
+                     "no NCCL inside the PDHG loop",
+              "nccl": "NCCL all-gather(xbar) + reduce-scatter(A_g^T y) + all-reduce(3 scalars) per attempt",
+              "allreduce": "primal side replicated, one NCCL all-reduce of n+1 doubles per attempt"}
+
+
 def workload(args):
     from cuopt_b200 import lpgen
-    return lpgen.sparse_lp(args.rows, args.cols, args.nnz_per_row, seed=1234)
+    if args.workload == "c3":
+        return lpgen.multicommodity(nodes=9000, arcs=27000, commodities=11, seed=1234)
+    rows, cols = WORKLOADS[args.workload]
+    return lpgen.sparse_lp(args.rows or rows, args.cols or cols, args.nnz_per_row, seed=1234)
 
 
 def config_dict(args, lp, n_gpus):
-    return {"workload": f"configs[1]: synthetic random sparse LP {lp.m}x{lp.n}, {args.nnz_per_row} nnz/row, fp64, "
-                        f"planted optimum (cuopt_b200.lpgen.sparse_lp seed 1234)",
+    names = {"c4": "configs[3] instance (the 10M-var LP the metric is quoted on)", "c2": "configs[1]",
+             "c3": "configs[2] (pds-shaped multicommodity flow, synthesised: no pds file in the tree)"}
+    transport = os.environ.get("CUOPT_B200_DIST_MODE", "p2p")
+    return {"workload": f"{names[args.workload]}: {lp.name}, {lp.m}x{lp.n}, nnz {lp.nnz}, fp64",
             "rows": lp.m, "cols": lp.n, "nnz": lp.nnz, "iterations_per_step": args.iters,
             "pdlp_solver_mode": "Stable2",
-            "parallelism": (f"constraint rows sharded over {n_gpus} GPUs (one process each), primal side replicated, "
-                            f"one NCCL all-reduce of n+1 doubles per PDHG attempt") if n_gpus > 1 else "1 GPU",
+            "parallelism": (f"ONE LP: constraint rows and primal column slices sharded over {n_gpus} GPUs (one process "
+                            f"each); transport: {TRANSPORTS[transport]}") if n_gpus > 1 else "1 GPU",
             "l2_policy": "per-iteration working set (A, A^T, 14 vectors = %.0f MB) exceeds the 126 MB L2"
                          % (lp.algorithmic_bytes_per_iteration() / 1e6)}
 
@@ -125,14 +140,21 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--rows", type=int, default=1_000_000)
-    ap.add_argument("--cols", type=int, default=1_000_000)
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3"])
+    ap.add_argument("--rows", type=int, default=0, help="override the workload's row count (sparse_lp workloads)")
+    ap.add_argument("--cols", type=int, default=0)
     ap.add_argument("--nnz-per-row", type=int, default=8)
     ap.add_argument("--iters", type=int, default=ITERS_PER_STEP)
-    ap.add_argument("--cpu-iters", type=int, default=60, help="oracle iterations per step (CPU arm / cpu_baseline)")
+    ap.add_argument("--cpu-iters", type=int, default=0,
+                    help="oracle iterations per step (CPU arm / cpu_baseline); 0 = sized to ~20 s from the nnz count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gap-iteration-limit", type=int, default=8000,
+                    help="iteration cap of the untimed time-to-1e-6-gap solve reported in detail (0 = skip)")
     ap.add_argument("--profile-reps", type=int, default=200)
     args = ap.parse_args()
+    if args.cpu_iters <= 0:  # the OpenMP oracle runs roughly 1e8 nonzeros/s of PDHG iteration on 8 cores
+        nnz_guess = {"c4": 80e6, "c2": 8e6, "c3": 0.9e6}[args.workload]
+        args.cpu_iters = int(max(4, min(400, 1.5e8 / nnz_guess * 4)))
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
     if args.impl == "reference":
@@ -207,6 +229,24 @@ def main():
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         launches = int(c[0])  # `its` is NOT summed: all ranks iterate on ONE joint LP
 
+    # second half of BASELINE.json's metric: time to a 1e-6 relative gap (all six tolerances 1e-6), one solve through
+    # the same call as the timed steps, outside the timed region; collective at N > 1
+    to_gap = None
+    if args.gap_iteration_limit > 0:
+        gs = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False, iteration_limit=args.gap_iteration_limit)
+        gs.set("optimality_tolerance", 1e-6)
+        saved, settings = settings, gs
+        barrier()
+        tg = time.perf_counter()
+        gst, _ = one_step()
+        barrier()
+        tg = time.perf_counter() - tg
+        settings = saved
+        to_gap = {"tolerance": 1e-6, "wall_seconds": tg, "solver_loop_seconds": gst.pdhg_loop_seconds + gst.termination_seconds,
+                  "iterations": gst.number_of_steps_taken, "relative_gap": gst.relative_gap,
+                  "primal_objective": gst.primal_objective, "planted_optimum": lp.optimal_objective,
+                  "reached": bool(gst.relative_gap <= 1e-6 and gst.number_of_steps_taken < args.gap_iteration_limit)}
+
     # roofline of the dominant kernel, measured in situ with CUDA events on the solver's stream
     roof = None
     cpu = None
@@ -230,8 +270,8 @@ def main():
                                "algorithmic_GBps": b_iter / (prof.ms_iteration * 1e-3) / 1e9,
                                "frac_of_hbm_peak": b_iter / (prof.ms_iteration * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                  "grids": {"primal": prof.grid_primal, "dual": prof.grid_dual, "transpose": prof.grid_transpose},
-                 "setup_seconds_per_step": setup_s / args.steps}
-        if not args.no_cpu_baseline and world == 1 or (not args.no_cpu_baseline and rank == 0):
+                 "setup_seconds_per_step": setup_s / args.steps, "time_to_gap": to_gap}
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
             from oracle import pdlp_oracle as po
             o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=0.0)
             o.initialise(); o.run(5)

@@ -75,7 +75,7 @@ class dvec {
   }
   void copy_from(const dvec& o, cudaStream_t s)
   {
-    if (n_ != o.n_ || slack_ != o.slack_) resize(o.n_, o.slack_);
+    if (n_ != o.n_) resize(o.n_, o.slack_);  // same logical size: keep this buffer (it may be padded or peer-mapped)
     if (n_) CUOPT_CUDA_TRY(cudaMemcpyAsync(p_, o.p_, n_ * sizeof(T), cudaMemcpyDeviceToDevice, s));
   }
   T* data() { return p_; }

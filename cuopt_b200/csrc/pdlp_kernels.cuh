@@ -142,6 +142,57 @@ __device__ __forceinline__ void pdhg_step_rule(pdhg_ctl_t* ctl, double interacti
   *ctl        = s;
 }
 
+// ---- multi-GPU peer transport primitives (used by the column-sliced attempt further down) ----
+constexpr int DIST_MAX_PEERS        = 8;
+constexpr int DIST_FLAG_XBAR        = 0 * DIST_MAX_PEERS;  // flags[slot + g]: rank g's contribution has landed
+constexpr int DIST_FLAG_PARTIAL     = 1 * DIST_MAX_PEERS;
+constexpr int DIST_FLAG_SCALARS     = 2 * DIST_MAX_PEERS;
+constexpr int DIST_FLAG_COUNT       = 3 * DIST_MAX_PEERS;
+constexpr long long DIST_SPIN_LIMIT = 20000000000LL;  // ~10 s of SM clocks, then trap instead of hanging the box
+struct peer_ptrs_t {
+  double* p[DIST_MAX_PEERS];
+};
+struct peer_flags_t {
+  unsigned long long* p[DIST_MAX_PEERS];
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// whole CTA: returns once flags[0..count) have all reached `epoch`
+__device__ __forceinline__ void peer_wait(const unsigned long long* flags, int count, unsigned long long epoch)
+{
+  if ((int)threadIdx.x < count) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
+      __nanosleep(64);
+      if (clock64() - t0 > DIST_SPIN_LIMIT) __trap();
+    }
+  }
+  __syncthreads();
+}
+// whole CTA, after its last peer store: the last CTA of the grid raises flag `index` on every rank
+__device__ __forceinline__ void peer_signal_grid_done(unsigned* ticket, const peer_flags_t& flags, int world, int index,
+                                                      unsigned long long epoch)
+{
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const unsigned t = atomicAdd(ticket, 1u);
+  if (t != gridDim.x - 1) return;
+  *ticket = 0u;
+  __threadfence_system();
+#pragma unroll
+  for (int r = 0; r < DIST_MAX_PEERS; ++r)
+    if (r < world) st_release_sys(flags.p[r] + index, epoch);
+}
+
 // =============================================================================================
 // K1 — primal step.  x' = clamp(x - tau (c - A^T y), l, u), xbar = 2x' - x
 // (pdhg.cu:137-158 + utils.cuh:81-95), fused with the primal half of the running-average update
@@ -192,11 +243,15 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_dual_step(const
                                                                            const double* __restrict__ lc,
                                                                            const double* __restrict__ uc,
                                                                            double* __restrict__ sum_y,
-                                                                           double* __restrict__ part_dy2)
+                                                                           double* __restrict__ part_dy2,
+                                                                           const unsigned long long* xbar_flags,
+                                                                           int n_xbar_flags)
 {
   if (!ctl->active) return;
   __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
   __shared__ double red[32];
+  // multi-GPU peer transport: xbar slices arrive by NVLink stores of the other ranks' K1s (see k_primal_step_bcast)
+  if (xbar_flags) peer_wait(xbar_flags, n_xbar_flags, (unsigned long long)ctl->attempts + 1ull);
   const int cur      = ctl->parity;
   const double* y    = cur ? ybuf1 : ybuf0;
   double* yn         = cur ? ybuf0 : ybuf1;
@@ -348,6 +403,169 @@ __global__ void __launch_bounds__(EW_THREADS) k_interaction_step(pdhg_ctl_t* __r
   const double dx2         = gather_partials(parts + gridDim.x, gridDim.x, red);
   if (threadIdx.x != 0) return;
   pdhg_step_rule(ctl, interaction, dx2, __ldcg(buf + n));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column-sliced multi-GPU attempt (SURVEY §8e scheme (ii)): rank g owns rows R_g of A AND the slice
+// J_g = [g*nslice, (g+1)*nslice) of every primal vector.  Per attempt
+//   K1s   primal step on J_g; xbar slice -> every rank           (all-gather)
+//   K2    dual step on R_g (needs the full xbar)
+//   K3p   partial A_g^T y'_g over all n columns -> slice owners  (reduce-scatter)
+//   K3s   owner sums the G partials of its slice in rank order, interaction / movement partial sums
+//   rule  three scalars from every rank, summed in rank order -> identical accept/reject everywhere
+// Two transports: NCCL collectives between the kernels, or NVLink peer stores issued by the producing kernels
+// themselves (the transfer overlaps the SpMV row by row; flags replace the collectives, no NCCL in the loop).
+// Flags are monotone epochs (= attempt number), written with st.release.sys by the last CTA of the producer
+// after every CTA fenced its stores system-wide; consumers poll with ld.acquire.sys and read the payload
+// with ld.global.cg (L2 is the coherence point for peer writes).
+// ---------------------------------------------------------------------------------------------
+// K1s with the all-gather fused in: pointers are already offset to this rank's slice; xbar_peers.p[r] = rank r's
+// xbar + j0.
+__global__ void __launch_bounds__(EW_THREADS) k_primal_step_bcast(pdhg_ctl_t* __restrict__ ctl,
+                                                                  int nloc,
+                                                                  double* __restrict__ xbuf0,
+                                                                  double* __restrict__ xbuf1,
+                                                                  const double* __restrict__ aty0,
+                                                                  const double* __restrict__ aty1,
+                                                                  const double* __restrict__ c,
+                                                                  const double* __restrict__ l,
+                                                                  const double* __restrict__ u,
+                                                                  double* __restrict__ sum_x,
+                                                                  peer_ptrs_t xbar_peers,
+                                                                  peer_flags_t flags,
+                                                                  int world,
+                                                                  int rank)
+{
+  if (!ctl->active) return;
+  const unsigned long long epoch = (unsigned long long)ctl->attempts + 1ull;
+  const int cur      = ctl->parity;
+  const double* x    = cur ? xbuf1 : xbuf0;
+  double* xn         = cur ? xbuf0 : xbuf1;
+  const double* aty  = cur ? aty1 : aty0;
+  const double tau   = ctl->tau;
+  const bool pending = ctl->pending_avg != 0;
+  const double w     = ctl->pending_weight;
+  const int stride   = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nloc; j += stride) {
+    const double xj = x[j];
+    if (pending) sum_x[j] = sum_x[j] + w * xj;
+    const double gradient = ld_stream(c + j) - aty[j];
+    double next           = xj - (tau * gradient);
+    next                  = fmax(fmin(next, ld_stream(u + j)), ld_stream(l + j));
+    xn[j]                 = next;
+    const double xb       = next - xj + next;
+#pragma unroll
+    for (int r = 0; r < DIST_MAX_PEERS; ++r)
+      if (r < world) xbar_peers.p[r][j] = xb;
+  }
+  peer_signal_grid_done(&ctl->ticket[1], flags, world, DIST_FLAG_XBAR + rank, epoch);
+}
+
+// K3p with the reduce-scatter fused in: column j's partial goes straight to its owner's staging row of this rank;
+// stage_peers.p[h] = rank h's stage + rank * nslice.
+__global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_partial_scatter(pdhg_ctl_t* __restrict__ ctl,
+                                                                                           csr_warp_view_t AT,
+                                                                                           const double* __restrict__ ybuf0,
+                                                                                           const double* __restrict__ ybuf1,
+                                                                                           peer_ptrs_t stage_peers,
+                                                                                           int nslice,
+                                                                                           peer_flags_t flags,
+                                                                                           int world,
+                                                                                           int rank)
+{
+  if (!ctl->active) return;
+  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
+  const unsigned long long epoch = (unsigned long long)ctl->attempts + 1ull;
+  const double* yn               = ctl->parity ? ybuf0 : ybuf1;
+  struct payload_t {};
+  auto pre_op = [&](int) { return payload_t{}; };
+  auto row_op = [&](int j, double s, const payload_t&) {
+    const int h  = j / nslice;
+    double* base = stage_peers.p[0];
+#pragma unroll
+    for (int r = 1; r < DIST_MAX_PEERS; ++r)
+      if (h == r) base = stage_peers.p[r];
+    base[j - h * nslice] = s;
+  };
+  spmv_warp_rows<payload_t>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op);
+  peer_signal_grid_done(&ctl->ticket[2], flags, world, DIST_FLAG_PARTIAL + rank, epoch);
+}
+
+// K3s: A^T y' on this rank's slice = sum over the n_src staged partials (rank order), then the slice's share of
+// the interaction and ||dx||^2; the last CTA hands {interaction, ||dx||^2, ||dy||^2 of this rank's rows} to
+// every rank in scal_peers (p[r] = rank r's scalar table + 4 * rank) and raises the scalar flag.
+// NCCL transport: n_src = 1 (src = reduce-scatter output), world_out = 1, flags.p[0] = nullptr.
+__global__ void __launch_bounds__(EW_THREADS) k_interaction_slice(pdhg_ctl_t* __restrict__ ctl,
+                                                                  int nloc,
+                                                                  const double* __restrict__ src,
+                                                                  int n_src,
+                                                                  size_t src_stride,
+                                                                  const double* __restrict__ xbuf0,
+                                                                  const double* __restrict__ xbuf1,
+                                                                  double* __restrict__ aty0,
+                                                                  double* __restrict__ aty1,
+                                                                  double* __restrict__ parts,
+                                                                  const double* __restrict__ part_dy2,
+                                                                  int n_part_dy2,
+                                                                  const unsigned long long* wait_flags,
+                                                                  peer_ptrs_t scal_peers,
+                                                                  peer_flags_t flags,
+                                                                  int world_out,
+                                                                  int rank)
+{
+  if (!ctl->active) return;
+  __shared__ double red[32];
+  const unsigned long long epoch = (unsigned long long)ctl->attempts + 1ull;
+  if (wait_flags) peer_wait(wait_flags, n_src, epoch);
+  const int cur     = ctl->parity;
+  const double* x   = cur ? xbuf1 : xbuf0;
+  const double* xn  = cur ? xbuf0 : xbuf1;
+  const double* aty = cur ? aty1 : aty0;
+  double* atyn      = cur ? aty0 : aty1;
+  double acc[2]     = {0.0, 0.0};
+  const int stride  = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nloc; j += stride) {
+    double s = 0.0;
+    for (int g = 0; g < n_src; ++g) s += __ldcg(src + (size_t)g * src_stride + j);
+    atyn[j]        = s;
+    const double d = xn[j] - x[j];
+    acc[0] += d * (s - aty[j]);
+    acc[1] += d * d;
+  }
+  if (!publish_and_elect<2>(acc, parts, &ctl->ticket[0], red)) return;
+  const double interaction = gather_partials(parts, gridDim.x, red);
+  const double dx2         = gather_partials(parts + gridDim.x, gridDim.x, red);
+  const double dy2         = gather_partials(part_dy2, n_part_dy2, red);
+  if (threadIdx.x != 0) return;
+#pragma unroll
+  for (int r = 0; r < DIST_MAX_PEERS; ++r)
+    if (r < world_out) {
+      double* o = scal_peers.p[r];
+      o[0]      = interaction;
+      o[1]      = dx2;
+      o[2]      = dy2;
+    }
+  if (flags.p[0] == nullptr) return;
+  __threadfence_system();
+#pragma unroll
+  for (int r = 0; r < DIST_MAX_PEERS; ++r)
+    if (r < world_out) st_release_sys(flags.p[r] + DIST_FLAG_SCALARS + rank, epoch);
+}
+
+// Step rule from the n_src scalar triples (rank order).  One warp.
+__global__ void k_step_rule_gather(pdhg_ctl_t* __restrict__ ctl, const double* __restrict__ scal, int n_src,
+                                   const unsigned long long* wait_flags)
+{
+  if (!ctl->active) return;
+  if (wait_flags) peer_wait(wait_flags, n_src, (unsigned long long)ctl->attempts + 1ull);
+  if (threadIdx.x != 0) return;
+  double interaction = 0.0, dx2 = 0.0, dy2 = 0.0;
+  for (int g = 0; g < n_src; ++g) {
+    interaction += __ldcg(scal + 4 * g + 0);
+    dx2 += __ldcg(scal + 4 * g + 1);
+    dy2 += __ldcg(scal + 4 * g + 2);
+  }
+  pdhg_step_rule(ctl, interaction, dx2, dy2);
 }
 
 // Applies a still-pending running-average update (end of a batch, before averages are formed).

@@ -171,6 +171,21 @@ struct pdlp_solver_t::impl_t {
   dvec<double> dist_buf;  // row-sharded mode: partial A^T y' (+1 slot) / 2n for the evaluation, all-reduced in place
   const dist_context_t* dist = nullptr;
   bool sharded() const { return dist != nullptr && dist->world > 1; }
+  // Transport of the sharded PDHG attempt: 0 = replicated primal side + one all-reduce (scheme (i)),
+  // 1 = column slices + NCCL all-gather / reduce-scatter (scheme (ii)), 2 = column slices + NVLink peer stores
+  // issued by the producing kernels (scheme (ii), no NCCL in the loop).  CUOPT_B200_DIST_MODE=allreduce|nccl|p2p.
+  enum { DIST_ALLREDUCE = 0, DIST_NCCL_SLICES = 1, DIST_P2P = 2 };
+  int dist_mode = DIST_ALLREDUCE;
+  int nslice = 0, n_pad = 0, slice_j0 = 0, slice_n = 0, grid_slice = 1;
+  dvec<double> rs_buf, stage, scal;
+  dvec<unsigned long long> d_flags;
+  void* xbar_peer[DIST_MAX_PEERS]  = {};
+  void* stage_peer[DIST_MAX_PEERS] = {};
+  void* scal_peer[DIST_MAX_PEERS]  = {};
+  void* flag_peer[DIST_MAX_PEERS]  = {};
+  bool peers_open = false;
+  peer_ptrs_t p_xbar{}, p_stage{}, p_scal{};
+  peer_flags_t p_flags{};
   dvec<unsigned> d_ticket;
   dvec<pdhg_ctl_t> d_ctl;
   dvec<eval_t> d_eval;
@@ -195,8 +210,26 @@ struct pdlp_solver_t::impl_t {
   double t_start  = 0.0;
   long long launches = 0;
 
+  // Peer mappings must be gone everywhere before any rank frees the memory behind them.  Collective when
+  // `collective` (end of a solve: every rank gets here); the destructor alone can only close its own side.
+  void close_peer_memory(bool collective)
+  {
+    if (!peers_open) return;
+    cudaStreamSynchronize(stream);
+    dist->close_peers(xbar_peer);
+    dist->close_peers(stage_peer);
+    dist->close_peers(scal_peer);
+    dist->close_peers(flag_peer);
+    peers_open = false;
+    if (collective) {
+      dist->allreduce(d_scalar.data(), 1, true, stream);  // barrier
+      cudaStreamSynchronize(stream);
+    }
+  }
+
   ~impl_t()
   {
+    close_peer_memory(false);
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
     if (ev_a) cudaEventDestroy(ev_a);
     if (ev_b) cudaEventDestroy(ev_b);
@@ -256,12 +289,23 @@ struct pdlp_solver_t::impl_t {
     c.upload(hc, stream); l.upload(hl, stream); u.upload(hu, stream); lc.upload(hlc, stream); uc.upload(huc, stream);
     cs.copy_from(c, stream); ls.copy_from(l, stream); us.copy_from(u, stream); lcs.copy_from(lc, stream); ucs.copy_from(uc, stream);
 
-    for (int b = 0; b < 2; ++b) {
-      xbuf[b].resize(n); xbuf[b].zero(stream);
-      ybuf[b].resize(m); ybuf[b].zero(stream);
-      atybuf[b].resize(n); atybuf[b].zero(stream);
+    // sharded: primal vectors that travel by all-gather are padded to world * nslice (the pad is never read as data)
+    size_t pad = 0;
+    if (sharded()) {
+      if (dist->world > DIST_MAX_PEERS) throw lp_error(error_type_t::ValidationError, "at most 8 ranks per solve");
+      nslice   = (((n + dist->world - 1) / dist->world) + 31) & ~31;
+      n_pad    = nslice * dist->world;
+      slice_j0 = std::min(n, dist->rank * nslice);
+      slice_n  = std::max(0, std::min(nslice, n - slice_j0));
+      pad      = (size_t)(n_pad - n);
     }
-    for (dvec<double>* v : {&xbar, &sum_x, &x_avg, &x_lr, &rc_cur, &rc_avg, &scratch_n}) { v->resize(n); v->zero(stream); }
+    for (int b = 0; b < 2; ++b) {
+      xbuf[b].resize(n, pad); xbuf[b].zero(stream);
+      ybuf[b].resize(m); ybuf[b].zero(stream);
+      atybuf[b].resize(n, pad); atybuf[b].zero(stream);
+    }
+    for (dvec<double>* v : {&xbar, &sum_x}) { v->resize(n, pad); v->zero(stream); }
+    for (dvec<double>* v : {&x_avg, &x_lr, &rc_cur, &rc_avg, &scratch_n}) { v->resize(n); v->zero(stream); }
     for (dvec<double>* v : {&sum_y, &y_avg, &y_lr, &scratch_m}) { v->resize(m); v->zero(stream); }
     Dr.resize(m);
     Dc.resize(n);
@@ -289,12 +333,12 @@ struct pdlp_solver_t::impl_t {
     grid_k1   = grid_n;
     grid_misc = ew_grid(std::max(n, m), sms);
     part_dy2.resize(grid_k2);
-    part_k3.resize(2 * (size_t)grid_k3);
+    part_k3.resize(2 * (size_t)std::max(grid_k3, grid_n));
     part_rows.resize(6 * (size_t)grid_er);
     part_cols.resize(8 * (size_t)std::max(grid_ec, grid_n));
     part_misc.resize(2 * (size_t)std::max(grid_misc, ew_grid(nnz, sms)));
-    if (sharded()) { dist_buf.resize(2 * (size_t)n + 8); dist_buf.zero(stream); use_graphs = false; }
     d_scalar.resize(8);
+    if (sharded()) setup_transport();
     d_ticket.resize(4);
     d_ticket.zero(stream);
     d_ctl.resize(1);
@@ -302,6 +346,54 @@ struct pdlp_solver_t::impl_t {
     d_eval.resize(2);
     d_eval.zero(stream);
     sync();
+  }
+
+  // sharded solve: pick the transport of the PDHG attempt and set up its buffers (collective)
+  void setup_transport()
+  {
+    dist_buf.resize(2 * (size_t)std::max(n, n_pad) + 8);
+    dist_buf.zero(stream);
+    dist_mode = DIST_P2P;
+    if (const char* e = std::getenv("CUOPT_B200_DIST_MODE")) {
+      const std::string v(e);
+      if (v == "allreduce") dist_mode = DIST_ALLREDUCE;
+      else if (v == "nccl") dist_mode = DIST_NCCL_SLICES;
+      else if (v == "p2p") dist_mode = DIST_P2P;
+      else throw lp_error(error_type_t::InvalidArgument, "CUOPT_B200_DIST_MODE must be allreduce, nccl or p2p");
+    }
+    grid_slice = ew_grid(std::max(nslice, 1), sms);
+    scal.resize(4 * DIST_MAX_PEERS);
+    scal.zero(stream);
+    if (dist_mode == DIST_NCCL_SLICES) { rs_buf.resize(nslice); rs_buf.zero(stream); }
+    if (dist_mode == DIST_P2P) {
+      stage.resize((size_t)nslice * dist->world);
+      stage.zero(stream);
+      d_flags.resize(DIST_FLAG_COUNT);
+      d_flags.zero(stream);
+      // every rank's buffers are zeroed (stream order) before its handles leave through the stream-ordered all-gather
+      bool ok = dist->open_peers(xbar.data(), xbar_peer, stream);
+      ok      = ok && dist->open_peers(stage.data(), stage_peer, stream);
+      ok      = ok && dist->open_peers(scal.data(), scal_peer, stream);
+      ok      = ok && dist->open_peers(d_flags.data(), flag_peer, stream);
+      if (!ok) {  // unanimous (open_peers agrees across ranks): no peer access on this box -> NCCL transport
+        dist->close_peers(xbar_peer); dist->close_peers(stage_peer); dist->close_peers(scal_peer);
+        dist_mode = DIST_NCCL_SLICES;
+        rs_buf.resize(nslice);
+        rs_buf.zero(stream);
+      } else {
+        peers_open = true;
+        for (int r = 0; r < dist->world; ++r) {
+          p_xbar.p[r]  = static_cast<double*>(xbar_peer[r]) + slice_j0;
+          p_stage.p[r] = static_cast<double*>(stage_peer[r]) + (size_t)dist->rank * nslice;
+          p_scal.p[r]  = static_cast<double*>(scal_peer[r]) + 4 * dist->rank;
+          p_flags.p[r] = static_cast<unsigned long long*>(flag_peer[r]);
+        }
+      }
+    }
+    if (dist_mode != DIST_P2P) {
+      use_graphs  = false;  // NCCL calls between the kernels
+      p_scal.p[0] = scal.data();
+    }
   }
 
   // deterministic setup reduction, result on the host
@@ -412,13 +504,54 @@ struct pdlp_solver_t::impl_t {
   }
 
   // ------------------------------------------------------------------------------ PDHG batches
+  // scheme (ii): this rank updates only its slice of the primal side (kernel comments in pdlp_kernels.cuh)
+  void enqueue_sliced_attempt()
+  {
+    const int j0 = slice_j0, G = dist->world, rk = dist->rank;
+    double *x0 = xbuf[0].data() + j0, *x1 = xbuf[1].data() + j0, *a0 = atybuf[0].data() + j0, *a1 = atybuf[1].data() + j0;
+    if (dist_mode == DIST_P2P) {
+      k_primal_step_bcast<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, x0, x1, a0, a1, cs.data() + j0,
+                                                                 ls.data() + j0, us.data() + j0, sum_x.data() + j0, p_xbar,
+                                                                 p_flags, G, rk);
+      k_dual_step<<<grid_k2, WARP_THREADS, 0, stream>>>(d_ctl.data(), As.warp_view(), xbar.data(), ybuf[0].data(),
+                                                        ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(), part_dy2.data(),
+                                                        d_flags.data() + DIST_FLAG_XBAR, G);
+      k_transpose_partial_scatter<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(),
+                                                                        ybuf[1].data(), p_stage, nslice, p_flags, G, rk);
+      k_interaction_slice<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, stage.data(), G, (size_t)nslice, x0, x1,
+                                                                 a0, a1, part_k3.data(), part_dy2.data(), grid_k2,
+                                                                 d_flags.data() + DIST_FLAG_PARTIAL, p_scal, p_flags, G, rk);
+      k_step_rule_gather<<<1, 32, 0, stream>>>(d_ctl.data(), scal.data(), G, d_flags.data() + DIST_FLAG_SCALARS);
+      return;
+    }
+    k_primal_step<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, x0, x1, a0, a1, cs.data() + j0,
+                                                         ls.data() + j0, us.data() + j0, sum_x.data() + j0,
+                                                         xbar.data() + j0);
+    dist->allgather(xbar.data(), nslice, stream);
+    k_dual_step<<<grid_k2, WARP_THREADS, 0, stream>>>(d_ctl.data(), As.warp_view(), xbar.data(), ybuf[0].data(), ybuf[1].data(),
+                                                      lcs.data(), ucs.data(), sum_y.data(), part_dy2.data(), nullptr, 0);
+    k_transpose_partial<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
+                                                              dist_buf.data());
+    dist->reduce_scatter(dist_buf.data(), rs_buf.data(), nslice, stream);
+    peer_flags_t no_flags{};
+    k_interaction_slice<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, rs_buf.data(), 1, 0, x0, x1, a0, a1,
+                                                               part_k3.data(), part_dy2.data(), grid_k2, nullptr, p_scal,
+                                                               no_flags, 1, rk);
+    dist->allreduce(scal.data(), 3, false, stream);
+    k_step_rule_gather<<<1, 32, 0, stream>>>(d_ctl.data(), scal.data(), 1, nullptr);
+  }
+
   void enqueue_attempt()
   {
+    if (sharded() && dist_mode != DIST_ALLREDUCE) {
+      enqueue_sliced_attempt();
+      return;
+    }
     k_primal_step<<<grid_k1, EW_THREADS, 0, stream>>>(d_ctl.data(), n, xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
                                                       atybuf[1].data(), cs.data(), ls.data(), us.data(), sum_x.data(),
                                                       xbar.data());
     k_dual_step<<<grid_k2, WARP_THREADS, 0, stream>>>(d_ctl.data(), As.warp_view(), xbar.data(), ybuf[0].data(), ybuf[1].data(),
-                                                      lcs.data(), ucs.data(), sum_y.data(), part_dy2.data());
+                                                      lcs.data(), ucs.data(), sum_y.data(), part_dy2.data(), nullptr, 0);
     if (!sharded()) {
       k_transpose_step<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
                                                              xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
@@ -437,7 +570,7 @@ struct pdlp_solver_t::impl_t {
   void launch_attempts(int count)
   {
     if (count <= 0) return;
-    launches += (sharded() ? 5LL : 3LL) * count;
+    launches += (sharded() ? 5LL : 3LL) * count;  // kernels; collectives are not counted
     if (!use_graphs || count == 1) {
       for (int i = 0; i < count; ++i) enqueue_attempt();
       check_launch();
@@ -481,14 +614,25 @@ struct pdlp_solver_t::impl_t {
     while (true) {
       // a couple of spare attempts cover the occasional rejected step without another round trip
       launch_attempts(todo + (todo >= 16 ? 2 : 0));
-      k_flush_average<<<grid_misc, EW_THREADS, 0, stream>>>(d_ctl.data(), n, xbuf[0].data(), xbuf[1].data(), sum_x.data(),
-                                                            m, ybuf[0].data(), ybuf[1].data(), sum_y.data());
+      const bool sliced = sharded() && dist_mode != DIST_ALLREDUCE;
+      const int fj0 = sliced ? slice_j0 : 0, fn = sliced ? slice_n : n;
+      k_flush_average<<<grid_misc, EW_THREADS, 0, stream>>>(d_ctl.data(), fn, xbuf[0].data() + fj0, xbuf[1].data() + fj0,
+                                                            sum_x.data() + fj0, m, ybuf[0].data(), ybuf[1].data(),
+                                                            sum_y.data());
       k_clear_pending<<<1, 1, 0, stream>>>(d_ctl.data());
       launches += 3;
       check_launch();
       fetch_ctl();
       if (h_ctl->valid == -1 || h_ctl->accepted >= target) break;
       todo = target - h_ctl->accepted;
+    }
+    if (sharded() && dist_mode != DIST_ALLREDUCE) {
+      // back to the replicated representation the major-iteration code works on: every rank receives the other
+      // slices of the current iterate, its A^T y and the running sum (3 all-gathers per batch of ~40 attempts)
+      const int cur = h_ctl->parity;
+      dist->allgather(xbuf[cur].data(), nslice, stream);
+      dist->allgather(atybuf[cur].data(), nslice, stream);
+      dist->allgather(sum_x.data(), nslice, stream);
     }
     CUOPT_CUDA_TRY(cudaEventRecord(ev_b, stream));
     CUOPT_CUDA_TRY(cudaEventSynchronize(ev_b));
@@ -780,6 +924,7 @@ lp_solution_t pdlp_solver_t::run()
   const double t0  = now_seconds();
   s.t_start        = t0;
   s.outer_loop(-1);
+  s.close_peer_memory(true);
   s.sol.stats.solve_time = now_seconds() - t0;
   return s.sol;
 }
@@ -871,7 +1016,7 @@ kernel_profile_t pdlp_solver_t::profile_kernels(int warmup_steps, int reps)
     cudaEventRecord(ev[1], s.stream);
     k_dual_step<<<s.grid_k2, WARP_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.As.warp_view(), s.xbar.data(), s.ybuf[0].data(),
                                                           s.ybuf[1].data(), s.lcs.data(), s.ucs.data(), s.sum_y.data(),
-                                                          s.part_dy2.data());
+                                                          s.part_dy2.data(), nullptr, 0);
     cudaEventRecord(ev[2], s.stream);
     k_transpose_step<<<s.grid_k3, WARP_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.ATs.warp_view(), s.ybuf[0].data(),
                                                                s.ybuf[1].data(), s.xbuf[0].data(), s.xbuf[1].data(),

@@ -67,3 +67,38 @@ def reference_protocol_step(shard, x, x_next, aty, y_local, sigma, lc, uc, allre
     aty_next, dy2 = buf[:-1], float(buf[-1])
     dx = x_next - x
     return y_next, aty_next, float(dx @ (aty_next - aty)), float(dx @ dx), dy2
+
+
+def slice_bounds(n: int, world: int):
+    """Column slices of the primal side in the sliced schemes: nslice = ceil(n / world) rounded up to 32 (the padded
+    length world * nslice is what the all-gathers move); rank g owns [g * nslice, min(n, (g + 1) * nslice))."""
+    nslice = (((n + world - 1) // world) + 31) & ~31
+    return nslice, [(min(n, g * nslice), min(n, (g + 1) * nslice)) for g in range(world)]
+
+
+def reference_protocol_step_sliced(shard, rank, world, x_slice, x_next_slice, aty_slice, y_local, sigma, lc, uc,
+                                   allgather, reduce_scatter_sum, allgather_scalars):
+    """One attempt of the column-sliced scheme (scheme (ii)) in numpy: this rank holds rows R_g of A and
+    the slice J_g of x, x', A^T y.  Exchanges: xbar slices -> everyone; partial A_g^T y'_g -> slice owners (summed in
+    RANK ORDER, as the peer-store transport does); three scalars per rank -> everyone (summed in rank order).
+    Returns (y_next_local, aty_next_slice, interaction, ||dx||^2, ||dy||^2) with the scalars identical on all ranks."""
+    A = shard
+    n = A.shape[1]
+    nslice, bounds = slice_bounds(n, world)
+    j0, j1 = bounds[rank]
+    xbar_slice = np.zeros(nslice)
+    xbar_slice[: j1 - j0] = x_next_slice - x_slice + x_next_slice
+    xbar = allgather(xbar_slice)[:n]                      # world * nslice doubles, pad dropped
+    ybar = y_local - sigma * (A @ xbar)
+    y_next = np.maximum(ybar + sigma * lc, np.minimum(ybar + sigma * uc, 0.0))
+    dy = y_next - y_local
+    partial = np.zeros(world * nslice)
+    partial[:n] = A.T @ y_next
+    aty_next_slice = reduce_scatter_sum(partial)[: j1 - j0]   # this rank's slice of the rank-ordered sum
+    dx = x_next_slice - x_slice
+    mine = np.array([float(dx @ (aty_next_slice - aty_slice)), float(dx @ dx), float(dy @ dy)])
+    table = allgather_scalars(mine)                      # world x 3, rank order
+    tot = np.zeros(3)
+    for g in range(world):
+        tot += table[g]
+    return y_next, aty_next_slice, float(tot[0]), float(tot[1]), float(tot[2])

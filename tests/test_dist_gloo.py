@@ -3,7 +3,10 @@
   * the ONE collective an attempt needs (all-reduce of [A_g^T y'_g ; ||dy_g||^2]) reproduces the single-process
     quantities of the oracle's attempt (A^T y', interaction, movement terms),
   * every rank derives bit-identical scalars from the all-reduced buffer (=> identical accept/reject decisions).
-The CUDA side of the same protocol is exercised by tests/test_gpu_dist.py on >= 2 GPUs."""
+  * the column-sliced scheme (all-gather of xbar slices, rank-ordered reduce-scatter of the partials, rank-ordered sum
+    of three scalars per rank) reproduces the same attempt and the same bits on every rank,
+  * the slice bounds tile [0, n) with 32-aligned slices.
+The CUDA side of the same protocols is exercised by tests/test_gpu_dist.py on >= 2 GPUs."""
 import os
 import socket
 
@@ -59,7 +62,42 @@ def _worker(rank, world, port, q):
         g = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
         dist.all_gather(g, torch.tensor([inter, dx2, dy2], dtype=torch.float64))
         same = all(torch.equal(g[0], t) for t in g)
-        q.put((rank, bool(ok), bool(same), r0, r1))
+        # column-sliced scheme (ii): all-gather of xbar slices, reduce-scatter of the partials in rank order,
+        # three scalars per rank summed in rank order
+        nslice, bounds = cdist.slice_bounds(lp.n, world)
+        j0, j1 = bounds[rank]
+
+        def allgather(buf):
+            g = [torch.zeros(len(buf), dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(g, torch.from_numpy(buf.copy()))
+            return torch.cat(g).numpy()
+
+        def reduce_scatter_sum(buf):  # gloo has no reduce_scatter: gather every rank's piece for me, add in rank order
+            full = [torch.zeros(world * nslice, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(full, torch.from_numpy(buf.copy()))
+            got = [f[rank * nslice:(rank + 1) * nslice] for f in full]
+            out = torch.zeros(nslice, dtype=torch.float64)
+            for g in range(world):
+                out += got[g]
+            return out.numpy()
+
+        def allgather_scalars(v):
+            g = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(g, torch.from_numpy(v.copy()))
+            return torch.stack(g).numpy()
+
+        y2, aty2, inter2, dx22, dy22 = cdist.reference_protocol_step_sliced(
+            As[r0:r1].tocsr(), rank, world, x[j0:j1], want["x_next"][j0:j1], aty[j0:j1], y[r0:r1], sigma, lcs[r0:r1],
+            ucs[r0:r1], allgather, reduce_scatter_sum, allgather_scalars)
+        ok2 = (np.allclose(y2, want["y_next"][r0:r1], rtol=1e-12, atol=1e-13)
+               and np.allclose(aty2, want["aty_next"][j0:j1], rtol=1e-11, atol=1e-12)
+               and abs(dx22 - want["norm_dx2"]) <= 1e-11 * want["norm_dx2"]
+               and abs(dy22 - want["norm_dy2"]) <= 1e-11 * want["norm_dy2"]
+               and abs(inter2 - want["interaction"]) <= 1e-9 * max(abs(want["interaction"]), want["norm_dx2"]))
+        g2 = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(g2, torch.tensor([inter2, dx22, dy22], dtype=torch.float64))
+        same2 = all(torch.equal(g2[0], t) for t in g2)
+        q.put((rank, bool(ok and ok2), bool(same and same2), r0, r1))
     finally:
         dist.destroy_process_group()
 
@@ -106,3 +144,12 @@ def test_shards_reassemble_the_matrix():
         assert np.array_equal(clb, lp.con_lb[r0:r1]) and np.array_equal(cub, lp.con_ub[r0:r1])
     A = sp.csr_matrix((lp.values, lp.indices, lp.offsets), shape=(lp.m, lp.n))
     assert (sp.vstack(rows) != A).nnz == 0
+
+
+def test_slice_bounds_tile_the_columns():
+    for n, world in [(1000, 2), (1000, 3), (31, 4), (10_000_000, 8), (64, 8), (5, 8)]:
+        nslice, b = cdist.slice_bounds(n, world)
+        assert nslice % 32 == 0 and nslice * world >= n
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        assert all(0 <= hi - lo <= nslice for lo, hi in b)

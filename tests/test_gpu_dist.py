@@ -15,17 +15,18 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q, size, tol, mode):
+def _worker(rank, world, port, q, size, tol, mode, transport):
     import torch
     import torch.distributed as dist
 
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      CUOPT_B200_DIST_MODE=transport)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from cuopt_b200 import capi, lpgen
         from cuopt_b200 import dist as cdist
-        lp = lpgen.sparse_lp(size, size, 8, seed=21)
+        lp = lpgen.sparse_lp(size, size + 37, 8, seed=21)  # n not a multiple of the slice width
         comm = cdist.bootstrap(rank, world, device=torch.device("cuda", rank))
         p, (r0, r1) = cdist.local_problem(lp, rank, world)
         s = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False, pdlp_solver_mode=mode)
@@ -40,44 +41,82 @@ def _worker(rank, world, port, q, size, tol, mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", [1, 3])
-def test_two_gpu_solve_matches_single_gpu(mode):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def _solve_on_gpus(world, size, tol, mode, transport):
     import torch.multiprocessing as mp
-
-    from cuopt_b200 import capi, lpgen
-    size, tol, world = 40_000, 1e-6, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, size, tol, mode)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, size, tol, mode, transport)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=600) for _ in range(world)), key=lambda d: d["rank"])
-    for p in procs:
-        p.join(120)
+    try:
+        res = sorted((q.get(timeout=300) for _ in range(world)), key=lambda d: d["rank"])
+        for p in procs:
+            p.join(60)
+    finally:
+        for p in procs:  # a rank that trapped or hung must not outlive the test
+            if p.is_alive():
+                p.kill()
     for r in res:
         assert r["rc"] == 0, r["err"]
-    # single-GPU solve of the whole LP in this process
-    lp = lpgen.sparse_lp(size, size, 8, seed=21)
+    # every rank reports the same status / iteration count / objectives / primal vector (identical decisions everywhere)
+    for r in res[1:]:
+        assert r["status"] == res[0]["status"] and r["its"] == res[0]["its"]
+        assert r["obj"] == res[0]["obj"] and r["dobj"] == res[0]["dobj"]
+        assert np.array_equal(r["x"], res[0]["x"])
+    return res
+
+
+def _single_gpu(size, tol, mode):
+    from cuopt_b200 import capi, lpgen
+    lp = lpgen.sparse_lp(size, size + 37, 8, seed=21)  # n not a multiple of the slice width
     p = capi.Problem.create_ranged(lp.offsets, lp.indices, lp.values, lp.con_lb, lp.con_ub, lp.c, lp.var_lb, lp.var_ub)
     s = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False, pdlp_solver_mode=mode)
     s.set("optimality_tolerance", tol)
     one = capi.solve(p, s)
-    st1 = one.stats()
     assert one.termination_status == 1
-    # every rank reports the same status / iteration count / objectives (identical decisions on all ranks)
-    assert res[0]["status"] == res[1]["status"] == 1
-    assert res[0]["its"] == res[1]["its"]
-    assert res[0]["obj"] == res[1]["obj"] and res[0]["dobj"] == res[1]["dobj"]
-    assert np.array_equal(res[0]["x"], res[1]["x"])
-    # and agrees with the single-GPU run: objective to 1e-6 (planted optimum known), iterations within a major period
+    return lp, one
+
+
+# transport of the sharded attempt: p2p = NVLink peer stores fused into the kernels (default), nccl = all-gather +
+# reduce-scatter, allreduce = replicated primal side (scheme (i))
+@pytest.mark.parametrize("mode,transport", [(1, "p2p"), (1, "nccl"), (1, "allreduce"), (3, "p2p")])
+def test_two_gpu_solve_matches_single_gpu(mode, transport):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    size, tol, world = 40_000, 1e-6, 2
+    res = _solve_on_gpus(world, size, tol, mode, transport)
+    lp, one = _single_gpu(size, tol, mode)
+    st1 = one.stats()
+    assert res[0]["status"] == 1
+    # agrees with the single-GPU run: objective to 1e-5 (planted optimum known; both stop at tolerance 1e-6),
+    # iteration count within a major period (the partial sums are added in a different order => not bit-identical)
     assert res[0]["obj"] == pytest.approx(lp.optimal_objective, rel=1e-5)
-    assert res[0]["obj"] == pytest.approx(st1.primal_objective, rel=1e-5)  # both stop at tolerance 1e-6
+    assert res[0]["obj"] == pytest.approx(st1.primal_objective, rel=1e-5)
+    assert res[0]["dobj"] == pytest.approx(st1.dual_objective, rel=1e-5)
     assert abs(res[0]["its"] - st1.number_of_steps_taken) <= max(40, 0.1 * st1.number_of_steps_taken)
-    # the dual blocks tile the dual vector
+    # the dual blocks tile the dual vector; both are tolerance-1e-6 points of a degenerate LP, so compare loosely
     y = np.concatenate([r["y"] for r in res])
     assert y.shape[0] == lp.m
-    assert np.max(np.abs(y - one.dual())) <= 1e-4 * max(1.0, np.max(np.abs(one.dual())))
+    y1 = one.dual()
+    assert np.linalg.norm(y - y1) <= 2e-3 * np.linalg.norm(y1)
+    assert np.linalg.norm(res[0]["x"] - one.primal()) <= 2e-3 * np.linalg.norm(one.primal())
+
+
+def test_peer_store_transport_is_deterministic_and_equals_nccl_transport():
+    """With two ranks a + b == b + a, so the peer-store transport (rank-ordered sums) and the NCCL transport must
+    produce bit-identical iterates; and the peer-store transport must reproduce itself run to run (no race between the
+    NVLink stores, the flags and the consuming kernels)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    size, tol, world = 40_000, 1e-6, 2
+    a = _solve_on_gpus(world, size, tol, 1, "p2p")
+    b = _solve_on_gpus(world, size, tol, 1, "p2p")
+    c = _solve_on_gpus(world, size, tol, 1, "nccl")
+    for other in (b, c):
+        assert other[0]["its"] == a[0]["its"]
+        assert other[0]["obj"] == a[0]["obj"] and other[0]["dobj"] == a[0]["dobj"]
+        assert np.array_equal(other[0]["x"], a[0]["x"])
+        assert all(np.array_equal(other[r]["y"], a[r]["y"]) for r in range(world))
