@@ -209,11 +209,12 @@ def main():
     if rank == 0:
         sampler.start()
     t0 = time.perf_counter()
-    its = 0; dev_s = 0.0; launches = 0; setup_s = 0.0
+    its = 0; dev_s = 0.0; launches = 0; setup_s = 0.0; loop_s = 0.0; term_s = 0.0
     for _ in range(args.steps):
         st, _ = one_step()
         its += st.number_of_steps_taken
         dev_s += st.pdhg_loop_seconds + st.termination_seconds
+        loop_s += st.pdhg_loop_seconds; term_s += st.termination_seconds
         setup_s += st.setup_seconds
         launches += st.kernel_launches
     barrier()
@@ -271,6 +272,9 @@ def main():
                                "frac_of_hbm_peak": b_iter / (prof.ms_iteration * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                  "grids": {"primal": prof.grid_primal, "dual": prof.grid_dual, "transpose": prof.grid_transpose},
                  "setup_seconds_per_step": setup_s / args.steps, "time_to_gap": to_gap}
+    if rank == 0:
+        extra["solver_seconds_per_step"] = {"pdhg_batches": loop_s / args.steps, "major_iterations": term_s / args.steps}
+        extra["transport"] = os.environ.get("CUOPT_B200_DIST_MODE", "p2p") if world > 1 else None
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
             from oracle import pdlp_oracle as po
             o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=0.0)

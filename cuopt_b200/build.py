@@ -49,11 +49,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd += ["-ccbin", host_cxx]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += sources() + ["-o", LIB, "-Xlinker", "-soname,libcuopt.so", "-ldl"]
+    tmp = LIB + ".tmp"  # link next to the target, then rename: a reader never sees a half-written library
+    cmd += sources() + ["-o", tmp, "-Xlinker", "-soname,libcuopt.so", "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed")
+    os.replace(tmp, LIB)
     if verbose:
         sys.stderr.write(res.stderr)
     return LIB

@@ -67,7 +67,17 @@ EXTENSION_SYMBOLS = [
     "cuOptB200SolverAdvance", "cuOptB200SolverGetScalar", "cuOptB200SolverGetVector", "cuOptB200SolverGetSolution",
     "cuOptB200SolverProfileKernels", "cuOptB200ReadProblem", "cuOptB200Version", "cuOptB200DistGetUniqueId",
     "cuOptB200DistInit", "cuOptB200DistDestroy", "cuOptB200SolveDistributed",
+    "cuOptB200SetWarmStartCapture", "cuOptB200GetWarmStart", "cuOptB200SetWarmStart", "cuOptB200CreateWarmStart",
+    "cuOptB200DestroyWarmStart", "cuOptB200WarmStartGetScalar", "cuOptB200WarmStartGetVector",
 ]
+WARM_VECTORS = ("current_primal_solution", "current_dual_solution", "initial_primal_average", "initial_dual_average",
+                "current_ATY", "sum_primal_solutions", "sum_dual_solutions", "last_restart_duality_gap_primal_solution",
+                "last_restart_duality_gap_dual_solution")
+WARM_IS_PRIMAL = (True, False, True, False, True, True, False, True, False)
+WARM_SCALARS = ("initial_primal_weight", "initial_step_size", "total_pdlp_iterations", "total_pdhg_iterations",
+                "last_candidate_kkt_score", "last_restart_kkt_score", "sum_solution_weight",
+                "iterations_since_last_restart")
+WARM_INT_SCALARS = ("total_pdlp_iterations", "total_pdhg_iterations", "iterations_since_last_restart")
 
 _lib = None
 
@@ -145,6 +155,14 @@ def lib():
         L.cuOptB200DistDestroy.argtypes = [C.POINTER(vp)]
         L.cuOptB200DistDestroy.restype = None
         L.cuOptB200SolveDistributed.argtypes = [vp, vp, vp, C.POINTER(vp)]
+        L.cuOptB200SetWarmStartCapture.argtypes = [vp, C.c_int32]
+        L.cuOptB200GetWarmStart.argtypes = [vp, C.POINTER(vp)]
+        L.cuOptB200SetWarmStart.argtypes = [vp, vp]
+        L.cuOptB200CreateWarmStart.argtypes = [C.c_int32, C.c_int32, C.POINTER(c_dbl_p), c_dbl_p, C.POINTER(vp)]
+        L.cuOptB200DestroyWarmStart.argtypes = [C.POINTER(vp)]
+        L.cuOptB200DestroyWarmStart.restype = None
+        L.cuOptB200WarmStartGetScalar.argtypes = [vp, C.c_char_p, c_dbl_p]
+        L.cuOptB200WarmStartGetVector.argtypes = [vp, C.c_char_p, c_dbl_p, c_int_p]
         _lib = L
     return _lib
 
@@ -300,6 +318,13 @@ class Settings:
         else:
             _check(lib().cuOptSetParameter(self.h, nb, str(value).encode()), name)
 
+    def capture_warm_start(self, enable: bool = True):
+        """Make solutions carry the state a later solve can continue from (cuOptB200SetWarmStartCapture)."""
+        _check(lib().cuOptB200SetWarmStartCapture(self.h, int(enable)))
+
+    def set_warm_start(self, warm_start: "WarmStart | None"):
+        _check(lib().cuOptB200SetWarmStart(self.h, warm_start.h if warm_start is not None else None))
+
     def get_float(self, name):
         v = C.c_double()
         _check(lib().cuOptGetFloatParameter(self.h, name.encode(), C.byref(v)), name)
@@ -372,6 +397,54 @@ class Solution:
         s = LPStats()
         _check(lib().cuOptB200GetLPStats(self.h, C.byref(s)))
         return s
+
+    def warm_start(self) -> "WarmStart":
+        h = C.c_void_p()
+        _check(lib().cuOptB200GetWarmStart(self.h, C.byref(h)), "cuOptB200GetWarmStart (was capture_warm_start set?)")
+        return WarmStart(h)
+
+
+class WarmStart:
+    """cuOptB200WarmStart handle: the reference's pdlp_warm_start_data_t through the C ABI."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def create(cls, m: int, n: int, data: dict) -> "WarmStart":
+        """From host arrays / scalars keyed by the reference's field names (see WARM_VECTORS, WARM_SCALARS)."""
+        vecs = [np.ascontiguousarray(data[k], np.float64) for k in WARM_VECTORS]
+        for v, primal, k in zip(vecs, WARM_IS_PRIMAL, WARM_VECTORS):
+            if len(v) != (n if primal else m):
+                raise ValueError(f"{k}: expected {n if primal else m} values, got {len(v)}")
+        ptrs = (c_dbl_p * 9)(*[_dp(v) for v in vecs])
+        sc = np.array([float(data[k]) for k in WARM_SCALARS])
+        h = C.c_void_p()
+        _check(lib().cuOptB200CreateWarmStart(m, n, ptrs, _dp(sc), C.byref(h)), "cuOptB200CreateWarmStart")
+        return cls(h)
+
+    def close(self):
+        if self.h and _lib is not None:
+            _lib.cuOptB200DestroyWarmStart(C.byref(self.h))
+
+    __del__ = close
+
+    def scalar(self, name: str):
+        v = C.c_double()
+        _check(lib().cuOptB200WarmStartGetScalar(self.h, name.encode(), C.byref(v)), name)
+        return int(v.value) if name in WARM_INT_SCALARS else v.value
+
+    def vector(self, name: str) -> np.ndarray:
+        size = C.c_int32()
+        _check(lib().cuOptB200WarmStartGetVector(self.h, name.encode(), None, C.byref(size)), name)
+        out = np.zeros(size.value)
+        _check(lib().cuOptB200WarmStartGetVector(self.h, name.encode(), _dp(out), C.byref(size)), name)
+        return out
+
+    def to_dict(self) -> dict:
+        d = {k: self.vector(k) for k in WARM_VECTORS}
+        d.update({k: self.scalar(k) for k in WARM_SCALARS})
+        return d
 
 
 def solve(problem: Problem, settings: Settings) -> Solution:

@@ -499,6 +499,109 @@ cuopt_int_t cuOptB200GetLPStats(cuOptSolution solution, cuOptB200LPStats* stats)
   return CUOPT_SUCCESS;
 }
 
+// ---- warm start (cuopt_b200_ext.h) ----
+namespace {
+struct warm_start_handle_t {
+  std::shared_ptr<const pdlp_warm_start_t> data;
+};
+const char* const WS_VECTORS[9] = {"current_primal_solution", "current_dual_solution", "initial_primal_average",
+                                   "initial_dual_average", "current_ATY", "sum_primal_solutions", "sum_dual_solutions",
+                                   "last_restart_duality_gap_primal_solution", "last_restart_duality_gap_dual_solution"};
+const bool WS_IS_PRIMAL[9]      = {true, false, true, false, true, true, false, true, false};
+std::vector<double> pdlp_warm_start_t::*const WS_MEMBERS[9] = {
+  &pdlp_warm_start_t::current_primal_solution, &pdlp_warm_start_t::current_dual_solution,
+  &pdlp_warm_start_t::initial_primal_average, &pdlp_warm_start_t::initial_dual_average, &pdlp_warm_start_t::current_ATY,
+  &pdlp_warm_start_t::sum_primal_solutions, &pdlp_warm_start_t::sum_dual_solutions,
+  &pdlp_warm_start_t::last_restart_duality_gap_primal_solution, &pdlp_warm_start_t::last_restart_duality_gap_dual_solution};
+}  // namespace
+
+cuopt_int_t cuOptB200SetWarmStartCapture(cuOptSolverSettings settings, cuopt_int_t enable)
+{
+  if (settings == nullptr) return CUOPT_INVALID_ARGUMENT;
+  static_cast<solver_settings_t*>(settings)->set_capture_warm_start(enable != 0);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptB200GetWarmStart(cuOptSolution solution, cuOptB200WarmStart* warm_start_ptr)
+{
+  SOLUTION_OR_FAIL(warm_start_ptr);
+  *warm_start_ptr = nullptr;
+  if (!s.sol.warm_start) return CUOPT_INVALID_ARGUMENT;
+  *warm_start_ptr = new warm_start_handle_t{s.sol.warm_start};
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptB200SetWarmStart(cuOptSolverSettings settings, cuOptB200WarmStart warm_start)
+{
+  if (settings == nullptr) return CUOPT_INVALID_ARGUMENT;
+  static_cast<solver_settings_t*>(settings)->set_warm_start(
+    warm_start ? static_cast<warm_start_handle_t*>(warm_start)->data : nullptr);
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptB200CreateWarmStart(cuopt_int_t num_constraints, cuopt_int_t num_variables,
+                                     const cuopt_float_t* const* vectors_9, const cuopt_float_t* scalars_8,
+                                     cuOptB200WarmStart* warm_start_ptr)
+{
+  if (warm_start_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  *warm_start_ptr = nullptr;
+  if (vectors_9 == nullptr || scalars_8 == nullptr || num_constraints < 0 || num_variables < 0) return CUOPT_INVALID_ARGUMENT;
+  for (int q = 0; q < 9; ++q)
+    if (vectors_9[q] == nullptr && (WS_IS_PRIMAL[q] ? num_variables : num_constraints) > 0) return CUOPT_INVALID_ARGUMENT;
+  try {
+    auto w = std::make_shared<pdlp_warm_start_t>();
+    for (int q = 0; q < 9; ++q) {
+      const int size = WS_IS_PRIMAL[q] ? num_variables : num_constraints;
+      ((*w).*WS_MEMBERS[q]).assign(vectors_9[q], vectors_9[q] + size);
+    }
+    w->initial_primal_weight         = scalars_8[0];
+    w->initial_step_size             = scalars_8[1];
+    w->total_pdlp_iterations         = (int)scalars_8[2];
+    w->total_pdhg_iterations         = (int)scalars_8[3];
+    w->last_candidate_kkt_score      = scalars_8[4];
+    w->last_restart_kkt_score        = scalars_8[5];
+    w->sum_solution_weight           = scalars_8[6];
+    w->iterations_since_last_restart = (int)scalars_8[7];
+    *warm_start_ptr                  = new warm_start_handle_t{w};
+  } catch (const std::bad_alloc&) {
+    return CUOPT_OUT_OF_MEMORY;
+  }
+  return CUOPT_SUCCESS;
+}
+void cuOptB200DestroyWarmStart(cuOptB200WarmStart* warm_start_ptr)
+{
+  if (warm_start_ptr == nullptr || *warm_start_ptr == nullptr) return;
+  delete static_cast<warm_start_handle_t*>(*warm_start_ptr);
+  *warm_start_ptr = nullptr;
+}
+cuopt_int_t cuOptB200WarmStartGetScalar(cuOptB200WarmStart warm_start, const char* name, cuopt_float_t* value_ptr)
+{
+  if (warm_start == nullptr || name == nullptr || value_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  const pdlp_warm_start_t& w = *static_cast<warm_start_handle_t*>(warm_start)->data;
+  const std::string s(name);
+  if (s == "initial_primal_weight") *value_ptr = w.initial_primal_weight;
+  else if (s == "initial_step_size") *value_ptr = w.initial_step_size;
+  else if (s == "total_pdlp_iterations") *value_ptr = w.total_pdlp_iterations;
+  else if (s == "total_pdhg_iterations") *value_ptr = w.total_pdhg_iterations;
+  else if (s == "last_candidate_kkt_score") *value_ptr = w.last_candidate_kkt_score;
+  else if (s == "last_restart_kkt_score") *value_ptr = w.last_restart_kkt_score;
+  else if (s == "sum_solution_weight") *value_ptr = w.sum_solution_weight;
+  else if (s == "iterations_since_last_restart") *value_ptr = w.iterations_since_last_restart;
+  else return CUOPT_INVALID_ARGUMENT;
+  return CUOPT_SUCCESS;
+}
+cuopt_int_t cuOptB200WarmStartGetVector(cuOptB200WarmStart warm_start, const char* name, cuopt_float_t* values,
+                                        cuopt_int_t* size_ptr)
+{
+  if (warm_start == nullptr || name == nullptr || size_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  const pdlp_warm_start_t& w = *static_cast<warm_start_handle_t*>(warm_start)->data;
+  for (int q = 0; q < 9; ++q) {
+    if (std::strcmp(name, WS_VECTORS[q]) != 0) continue;
+    const std::vector<double>& v = w.*WS_MEMBERS[q];
+    *size_ptr                    = (cuopt_int_t)v.size();
+    if (values != nullptr && !v.empty()) std::memcpy(values, v.data(), v.size() * sizeof(double));
+    return CUOPT_SUCCESS;
+  }
+  return CUOPT_INVALID_ARGUMENT;
+}
+
 cuopt_int_t cuOptB200SolverCreate(cuOptOptimizationProblem problem, cuOptSolverSettings settings, cuOptB200Solver* solver_ptr)
 {
   if (problem == nullptr || settings == nullptr || solver_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;

@@ -794,7 +794,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_eval_cols_from_aty(pdhg_ctl_t* _
 
 // Averages + in-place unscaling ahead of the evaluation (pdlp.cu:1103-1136,
 // weighted_average_solution.cu:114-142, initial_scaling.cu:456-484).
-// mode 0: avg := current (k_internal <= 1); mode 1: avg := sum / sum_weights (0 when nothing was summed)
+// mode 0: avg := current (k_internal <= 1); mode 1: avg := sum / sum_weights (0 when nothing was summed);
+// mode 2: avg untouched (first major iteration of a warm-started solve, pdlp.cu:1100-1129)
 __global__ void __launch_bounds__(EW_THREADS) k_average_and_unscale(const pdhg_ctl_t* __restrict__ ctl,
                                                                     int mode,
                                                                     int n,
@@ -808,10 +809,12 @@ __global__ void __launch_bounds__(EW_THREADS) k_average_and_unscale(const pdhg_c
   const int stride = gridDim.x * blockDim.x;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
     const double vj = v[j];
-    const double a  = mode == 0 ? vj : (empty ? 0.0 : sum_v[j] / sw);
     const double d  = scale[j];
-    avg[j]          = a * d;
-    v[j]            = vj * d;
+    if (mode != 2) {
+      const double a = mode == 0 ? vj : (empty ? 0.0 : sum_v[j] / sw);
+      avg[j]         = a * d;
+    }
+    v[j] = vj * d;
   }
 }
 // x /= D with 0 for D == 0 (eltwiseDivideCheckZero; initial_scaling.cu:411-427)

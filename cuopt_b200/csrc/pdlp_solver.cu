@@ -203,6 +203,7 @@ struct pdlp_solver_t::impl_t {
   bool initialised               = false;
   bool need_aty                  = true;   // first step, or first step after a restart to the average
   bool last_restart_was_average  = false;
+  bool warm_started              = false;  // pdlp.cu:1074: the first major iteration keeps the given averages
   double last_candidate_kkt      = 0.0, last_restart_kkt = 0.0;
   double l2_norm_b = 0.0, l2_norm_c = 0.0;
   lp_solution_t sol;
@@ -490,8 +491,9 @@ struct pdlp_solver_t::impl_t {
     k.primal_smoothing   = hp.primal_distance_smoothing;
     k.dual_smoothing     = hp.dual_distance_smoothing;
     *h_ctl               = k;
+    if (st.warm_start && !st.warm_start->empty()) apply_warm_start(*st.warm_start);
     CUOPT_CUDA_TRY(cudaMemcpyAsync(d_ctl.data(), h_ctl, sizeof(k), cudaMemcpyHostToDevice, stream));
-    if (hp.project_initial_primal) {  // pdlp.cu:1041-1056
+    if (hp.project_initial_primal) {  // pdlp.cu:1041-1056 (the unscaled average is clamped to the SCALED bounds there too)
       k_clamp<<<grid_n, EW_THREADS, 0, stream>>>(n, xbuf[0].data(), ls.data(), us.data());
       k_clamp<<<grid_n, EW_THREADS, 0, stream>>>(n, x_avg.data(), ls.data(), us.data());
     }
@@ -501,6 +503,84 @@ struct pdlp_solver_t::impl_t {
     sol.stats.initial_primal_weight = weight;
     sol.stats.setup_seconds += now_seconds() - t0;
     initialised = true;
+  }
+
+  // pdlp.cu:131-181 + :1010-1038: continue a previous solve.  Called with *h_ctl holding the fresh-start scalars.
+  void apply_warm_start(const pdlp_warm_start_t& w)
+  {
+    auto need = [&](const std::vector<double>& v, int size, const char* what) {
+      if ((int)v.size() != size)
+        throw lp_error(error_type_t::ValidationError, std::string("warm start: ") + what + " has the wrong size");
+    };
+    need(w.current_primal_solution, n, "current_primal_solution");
+    need(w.current_dual_solution, m, "current_dual_solution");
+    need(w.initial_primal_average, n, "initial_primal_average");
+    need(w.initial_dual_average, m, "initial_dual_average");
+    need(w.current_ATY, n, "current_ATY");
+    need(w.sum_primal_solutions, n, "sum_primal_solutions");
+    need(w.sum_dual_solutions, m, "sum_dual_solutions");
+    need(w.last_restart_duality_gap_primal_solution, n, "last_restart_duality_gap_primal_solution");
+    need(w.last_restart_duality_gap_dual_solution, m, "last_restart_duality_gap_dual_solution");
+    auto put = [&](dvec<double>& d, const std::vector<double>& h) {
+      if (!h.empty()) CUOPT_CUDA_TRY(cudaMemcpyAsync(d.data(), h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    };
+    put(xbuf[0], w.current_primal_solution);  // unscaled on arrival; update_primal_dual_solutions scales it (:963)
+    put(ybuf[0], w.current_dual_solution);
+    k_scale_back<<<grid_n, EW_THREADS, 0, stream>>>(n, xbuf[0].data(), Dc.data());
+    k_scale_back<<<grid_m, EW_THREADS, 0, stream>>>(m, ybuf[0].data(), Dr.data());
+    put(x_avg, w.initial_primal_average);
+    put(y_avg, w.initial_dual_average);
+    put(atybuf[0], w.current_ATY);
+    put(sum_x, w.sum_primal_solutions);
+    put(sum_y, w.sum_dual_solutions);
+    put(x_lr, w.last_restart_duality_gap_primal_solution);
+    put(y_lr, w.last_restart_duality_gap_dual_solution);
+    check_launch();
+    sync();  // the host vectors may go away with the settings object
+    pdhg_ctl_t& k       = *h_ctl;
+    k.step_size         = w.initial_step_size;
+    k.primal_weight     = w.initial_primal_weight;
+    k.tau               = k.step_size / k.primal_weight;
+    k.sigma             = k.step_size * k.primal_weight;
+    k.k_pdhg            = w.total_pdhg_iterations;
+    k.attempts          = w.total_pdhg_iterations;
+    k.sum_weights       = w.sum_solution_weight;
+    k.its_since_restart = w.iterations_since_last_restart;
+    total_pdlp_iterations = w.total_pdlp_iterations;
+    last_candidate_kkt    = w.last_candidate_kkt_score;
+    last_restart_kkt      = w.last_restart_kkt_score;
+    need_aty              = w.total_pdhg_iterations == 0;  // pdhg.cu:183: otherwise the given A^T y is the current one
+    warm_started          = true;
+  }
+
+  // pdlp.cu:469-489, at the moment a solution is returned: current iterate and averages are unscaled, the rest scaled
+  void capture_warm_start()
+  {
+    const int cur = h_ctl->parity;
+    auto w        = std::make_shared<pdlp_warm_start_t>();
+    auto get      = [&](std::vector<double>& h, const dvec<double>& d, int size) {
+      h.resize(size);
+      if (size) CUOPT_CUDA_TRY(cudaMemcpyAsync(h.data(), d.data(), (size_t)size * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    };
+    get(w->current_primal_solution, xbuf[cur], n);
+    get(w->current_dual_solution, ybuf[cur], m);
+    get(w->initial_primal_average, x_avg, n);
+    get(w->initial_dual_average, y_avg, m);
+    get(w->current_ATY, atybuf[cur], n);
+    get(w->sum_primal_solutions, sum_x, n);
+    get(w->sum_dual_solutions, sum_y, m);
+    get(w->last_restart_duality_gap_primal_solution, x_lr, n);
+    get(w->last_restart_duality_gap_dual_solution, y_lr, m);
+    sync();
+    w->initial_primal_weight         = h_ctl->primal_weight;
+    w->initial_step_size             = h_ctl->step_size;
+    w->total_pdlp_iterations         = total_pdlp_iterations;
+    w->total_pdhg_iterations         = h_ctl->attempts;
+    w->last_candidate_kkt_score      = last_candidate_kkt;
+    w->last_restart_kkt_score        = last_restart_kkt;
+    w->sum_solution_weight           = h_ctl->sum_weights;
+    w->iterations_since_last_restart = h_ctl->its_since_restart;
+    sol.warm_start                   = w;
   }
 
   // ------------------------------------------------------------------------------ PDHG batches
@@ -663,7 +743,8 @@ struct pdlp_solver_t::impl_t {
   void evaluate_iterates()
   {
     const int cur  = h_ctl->parity;
-    const int mode = (h_ctl->accepted <= 1) ? 0 : 1;
+    // pdlp.cu:1100-1129: warm start given and no step taken yet => the averages handed in are used as they are
+    const int mode = (warm_started && h_ctl->accepted == 0) ? 2 : (h_ctl->accepted <= 1) ? 0 : 1;
     k_average_and_unscale<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), mode, n, xbuf[cur].data(), sum_x.data(),
                                                              x_avg.data(), Dc.data());
     k_average_and_unscale<<<grid_m, EW_THREADS, 0, stream>>>(d_ctl.data(), mode, m, ybuf[cur].data(), sum_y.data(),
@@ -722,6 +803,7 @@ struct pdlp_solver_t::impl_t {
     s.final_step_size                         = h_ctl->step_size;
     s.final_primal_weight                     = h_ctl->primal_weight;
     s.kernel_launches                         = launches;
+    if (st.capture_warm_start) capture_warm_start();
     finished                                  = true;
   }
 

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <limits>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -138,6 +139,28 @@ struct pdlp_hyper_params_t {
   }
 };
 
+// Everything a later solve needs to continue this one where it stopped (reference:
+// include/cuopt/linear_programming/pdlp/pdlp_warm_start_data.hpp:28-72, filled by pdlp.cu:469-489 at termination,
+// consumed by pdlp.cu:131-181 / :1074-1136).  Spaces as in the reference: the current iterate and the averages are
+// UNSCALED (termination happens after the in-place unscaling), A^T y, the running sums and the last-restart point
+// live in the scaled space.  Host vectors; in a sharded solve the dual-side vectors cover this rank's rows.
+struct pdlp_warm_start_t {
+  std::vector<double> current_primal_solution, current_dual_solution;
+  std::vector<double> initial_primal_average, initial_dual_average;
+  std::vector<double> current_ATY;
+  std::vector<double> sum_primal_solutions, sum_dual_solutions;
+  std::vector<double> last_restart_duality_gap_primal_solution, last_restart_duality_gap_dual_solution;
+  double initial_primal_weight       = -1;
+  double initial_step_size           = -1;
+  int total_pdlp_iterations          = -1;
+  int total_pdhg_iterations          = -1;
+  double last_candidate_kkt_score    = -1;
+  double last_restart_kkt_score      = -1;
+  double sum_solution_weight         = -1;
+  int iterations_since_last_restart  = -1;
+  bool empty() const { return last_restart_duality_gap_dual_solution.empty(); }  // the reference's test, pdlp.cu:131
+};
+
 // pdlp_solver_settings_t as seen by the C ABI (solver_settings.cu:63-125 for defaults / ranges).
 struct pdlp_settings_t {
   double absolute_dual_tolerance     = 1e-4;
@@ -160,6 +183,9 @@ struct pdlp_settings_t {
   bool log_to_console                = true;
   bool crossover                     = false;
   std::string log_file, sol_file, user_problem_file;
+  // extension (cuopt_b200_ext.h): continue from a previous solve / make the solution carry the state to do so
+  std::shared_ptr<const pdlp_warm_start_t> warm_start;
+  bool capture_warm_start = false;
 };
 
 // additional_termination_information_t (pdlp/solver_solution.hpp:47-87) plus timing of this build.
@@ -195,6 +221,7 @@ struct lp_solution_t {
   std::string error_message;
   std::vector<double> primal, dual, reduced_cost;
   lp_stats_t stats;
+  std::shared_ptr<pdlp_warm_start_t> warm_start;  // filled when settings.capture_warm_start
 };
 
 }  // namespace cuopt_b200

@@ -25,6 +25,9 @@ class solver_settings_t {
   double get_float(const std::string& name) const;
 
   const pdlp_settings_t& pdlp() const { return pdlp_; }
+  // extension state that is not a named parameter (warm start, see cuopt_b200_ext.h)
+  void set_warm_start(std::shared_ptr<const pdlp_warm_start_t> w) { pdlp_.warm_start = std::move(w); }
+  void set_capture_warm_start(bool on) { pdlp_.capture_warm_start = on; }
 
  private:
   template <typename T>

@@ -103,6 +103,39 @@ cuopt_int_t cuOptB200SolveDistributed(cuOptOptimizationProblem local_rows_proble
                                       cuOptB200Dist dist,
                                       cuOptSolution* solution_ptr);
 
+/* ---- Warm start across solves --------------------------------------------------------------------------------
+ * The reference exposes pdlp_warm_start_data_t only through C++/Python
+ * (cpp/include/cuopt/linear_programming/pdlp/pdlp_warm_start_data.hpp:28-72, solver_settings.cu set_pdlp_warm_start_data,
+ * solver_solution.hpp get_pdlp_warm_start_data); these entry points carry it through the C ABI.
+ *   cuOptB200SetWarmStartCapture(settings, 1);  cuOptSolve(...);            // the solution now carries the state
+ *   cuOptB200GetWarmStart(solution, &ws);       cuOptB200SetWarmStart(settings2, ws);   cuOptSolve(...);
+ * Vector names: current_primal_solution, current_dual_solution, initial_primal_average, initial_dual_average,
+ * current_ATY, sum_primal_solutions, sum_dual_solutions, last_restart_duality_gap_primal_solution,
+ * last_restart_duality_gap_dual_solution.  Scalar names: initial_primal_weight, initial_step_size,
+ * total_pdlp_iterations, total_pdhg_iterations, last_candidate_kkt_score, last_restart_kkt_score,
+ * sum_solution_weight, iterations_since_last_restart.  The same scaling (same problem, same pdlp_solver_mode) is
+ * assumed, as in the reference. */
+typedef void* cuOptB200WarmStart;
+cuopt_int_t cuOptB200SetWarmStartCapture(cuOptSolverSettings settings, cuopt_int_t enable);
+/* new handle sharing the solution's state; CUOPT_INVALID_ARGUMENT when the solve did not capture it */
+cuopt_int_t cuOptB200GetWarmStart(cuOptSolution solution, cuOptB200WarmStart* warm_start_ptr);
+/* the settings keep a reference (the handle may be destroyed afterwards); NULL clears */
+cuopt_int_t cuOptB200SetWarmStart(cuOptSolverSettings settings, cuOptB200WarmStart warm_start);
+/* from raw host arrays: 9 vectors in the order listed above (primal-sized ones hold num_variables values, dual-sized
+ * ones num_constraints), 8 scalars in the order listed above */
+cuopt_int_t cuOptB200CreateWarmStart(cuopt_int_t num_constraints,
+                                     cuopt_int_t num_variables,
+                                     const cuopt_float_t* const* vectors_9,
+                                     const cuopt_float_t* scalars_8,
+                                     cuOptB200WarmStart* warm_start_ptr);
+void cuOptB200DestroyWarmStart(cuOptB200WarmStart* warm_start_ptr);
+cuopt_int_t cuOptB200WarmStartGetScalar(cuOptB200WarmStart warm_start, const char* name, cuopt_float_t* value_ptr);
+/* values == NULL: only *size_ptr is written */
+cuopt_int_t cuOptB200WarmStartGetVector(cuOptB200WarmStart warm_start,
+                                        const char* name,
+                                        cuopt_float_t* values,
+                                        cuopt_int_t* size_ptr);
+
 /* cuOptReadProblem with an explicit format switch (the reference C ABI always parses free format;
  * its C++ parse_mps(file, fixed_mps_format) has the flag: cpp/libmps_parser/include/mps_parser/parser.hpp:33). */
 cuopt_int_t cuOptB200ReadProblem(const char* filename, cuopt_int_t fixed_format, cuOptOptimizationProblem* problem_ptr);

@@ -230,6 +230,13 @@ class oracle_t {
   convergence_t conv_cur, conv_avg;
   bool initialised = false;
   int n_restarts = 0, n_major = 0;
+  // warm start handed in before initialise() (pdlp_warm_start_data.hpp:28-72): 9 vectors in the header's order
+  // {current primal, current dual, primal average, dual average, current A^T y, sum primal, sum dual,
+  //  last-restart primal, last-restart dual} and 8 scalars {primal weight, step size, total pdlp iterations,
+  //  total pdhg iterations, last candidate kkt, last restart kkt, sum of solution weights, iterations since restart}
+  bool warm_given = false;
+  std::vector<double> warm_v[9];
+  double warm_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<trace_row_t> trace;
   stats_t result{};
   std::vector<double> sol_x, sol_y, sol_rc;
@@ -386,6 +393,21 @@ class oracle_t {
     scale_problem();
     if (!hp.compute_initial_step_size_before_scaling) compute_initial_step_size(As);
     if (!hp.compute_initial_primal_weight_before_scaling) compute_initial_primal_weight(cs, lcs, ucs);
+    if (warm_given) {  // pdlp.cu:131-181 (state copied in) + :1010-1038 (scalars, initial solution scaled at :963)
+      x = warm_v[0]; y = warm_v[1];
+      scale_solutions(x, y);
+      x_avg = warm_v[2]; y_avg = warm_v[3];  // stay unscaled: the first major iteration uses them as they are
+      AtY = warm_v[4]; sum_x = warm_v[5]; sum_y = warm_v[6]; x_lr = warm_v[7]; y_lr = warm_v[8];
+      primal_weight      = warm_s[0];
+      step_size          = warm_s[1];
+      k_total            = (int)warm_s[2];
+      k_pdhg_host        = (int)warm_s[3];
+      k_pdhg_dev         = (int)warm_s[3];
+      last_candidate_kkt = warm_s[4];
+      last_restart_kkt   = warm_s[5];
+      sum_w              = warm_s[6];
+      its_since_restart  = (int)warm_s[7];
+    }
     tau   = step_size / primal_weight;  // adaptive_step_size_strategy.cu:348-366
     sigma = step_size * primal_weight;
     if (hp.project_initial_primal) {  // pdlp.cu:1041-1056, clamp = min(max(v, lo), hi) (utils.cuh:131-137)
@@ -692,7 +714,10 @@ class oracle_t {
         n_major += 1;
         trace_row_t tr{};
         tr.k = k_total;
-        if (k_internal <= 1) {  // :1110-1118
+        const bool no_rescale_average = k_internal == 0 && warm_given;  // :1100-1101
+        if (no_rescale_average) {
+          // the averages handed in with the warm start are already unscaled
+        } else if (k_internal <= 1) {  // :1110-1118
           x_avg = x;
           y_avg = y;
         } else {  // weighted_average_solution.cu:114-142
@@ -704,7 +729,7 @@ class oracle_t {
             for (int i = 0; i < m; ++i) y_avg[i] = sum_y[i] / sum_w;
           }
         }
-        unscale_solutions(x_avg, y_avg);  // :1131-1136
+        if (!no_rescale_average) unscale_solutions(x_avg, y_avg);  // :1131-1136
         unscale_solutions(x, y);
         const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         const bool done      = check_termination(elapsed);
@@ -786,6 +811,27 @@ void pdlp_oracle_convergence(void* h, const double* px, const double* py, double
   out8[3] = cv.dual_objective; out8[4] = cv.gap; out8[5] = cv.abs_objective; out8[6] = cv.status;
   out8[7] = o->primal_weight > 0 ? o->kkt_score(cv) : 0.0;
   if (reduced_cost) std::memcpy(reduced_cost, cv.reduced_cost.data(), sizeof(double) * o->n);
+}
+
+// Warm start (pdlp.cu:469-489 produce / :131-181 consume).  get: valid after a run() that returned 1 (x, y and the
+// averages are unscaled at that point, everything else scaled — exactly what the reference hands out).
+void pdlp_oracle_get_warm_start(void* h, double* const* vectors9, double* scalars8)
+{
+  auto* o = static_cast<oracle_t*>(h);
+  const std::vector<double>* v[9] = {&o->x, &o->y, &o->x_avg, &o->y_avg, &o->AtY, &o->sum_x, &o->sum_y, &o->x_lr, &o->y_lr};
+  for (int q = 0; q < 9; ++q) std::memcpy(vectors9[q], v[q]->data(), sizeof(double) * v[q]->size());
+  scalars8[0] = o->primal_weight; scalars8[1] = o->step_size; scalars8[2] = o->k_total; scalars8[3] = o->k_pdhg_host;
+  scalars8[4] = o->last_candidate_kkt; scalars8[5] = o->last_restart_kkt; scalars8[6] = o->sum_w;
+  scalars8[7] = o->its_since_restart;
+}
+// set: before initialise() / the first run()
+void pdlp_oracle_set_warm_start(void* h, const double* const* vectors9, const double* scalars8)
+{
+  auto* o = static_cast<oracle_t*>(h);
+  const bool primal[9] = {true, false, true, false, true, true, false, true, false};
+  for (int q = 0; q < 9; ++q) o->warm_v[q].assign(vectors9[q], vectors9[q] + (primal[q] ? o->n : o->m));
+  for (int q = 0; q < 8; ++q) o->warm_s[q] = scalars8[q];
+  o->warm_given = true;
 }
 
 // Named vectors / scalars for white-box comparisons.

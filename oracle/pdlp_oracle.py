@@ -140,6 +140,8 @@ def lib():
         _lib.pdlp_oracle_trace.restype = C.c_int
         _lib.pdlp_oracle_single_attempt.argtypes = [C.c_void_p] + [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_void_p] * 5
         _lib.pdlp_oracle_convergence.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        _lib.pdlp_oracle_get_warm_start.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.pdlp_oracle_set_warm_start.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -149,6 +151,16 @@ TERMINATION = {0: "NoTermination", 1: "Optimal", 2: "PrimalInfeasible", 3: "Dual
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+WARM_VECTORS = ("current_primal_solution", "current_dual_solution", "initial_primal_average", "initial_dual_average",
+                "current_ATY", "sum_primal_solutions", "sum_dual_solutions", "last_restart_duality_gap_primal_solution",
+                "last_restart_duality_gap_dual_solution")
+WARM_IS_PRIMAL = (True, False, True, False, True, True, False, True, False)
+WARM_SCALARS = ("initial_primal_weight", "initial_step_size", "total_pdlp_iterations", "total_pdhg_iterations",
+                "last_candidate_kkt_score", "last_restart_kkt_score", "sum_solution_weight",
+                "iterations_since_last_restart")
+WARM_INT_SCALARS = ("total_pdlp_iterations", "total_pdhg_iterations", "iterations_since_last_restart")
 
 
 class Oracle:
@@ -188,6 +200,24 @@ class Oracle:
         s = Stats()
         lib().pdlp_oracle_stats(self.h, C.byref(s))
         return s
+
+    # ---- warm start (pdlp_warm_start_data.hpp:28-72): dict with the header's field names ----
+    def get_warm_start(self) -> dict:
+        """State to continue from, as the reference hands it out at termination (pdlp.cu:469-489)."""
+        vecs = [np.zeros(self.n if p else self.m) for p in WARM_IS_PRIMAL]
+        ptrs = (C.c_void_p * 9)(*[v.ctypes.data for v in vecs])
+        sc = np.zeros(8)
+        lib().pdlp_oracle_get_warm_start(self.h, ptrs, _p(sc))
+        out = dict(zip(WARM_VECTORS, vecs))
+        out.update({k: (int(v) if k in WARM_INT_SCALARS else float(v)) for k, v in zip(WARM_SCALARS, sc)})
+        return out
+
+    def set_warm_start(self, w: dict):
+        """Before initialise() / the first run() (pdlp.cu:131-181)."""
+        self._warm = [np.ascontiguousarray(w[k], np.float64) for k in WARM_VECTORS]
+        ptrs = (C.c_void_p * 9)(*[v.ctypes.data for v in self._warm])
+        sc = np.array([float(w[k]) for k in WARM_SCALARS])
+        lib().pdlp_oracle_set_warm_start(self.h, ptrs, _p(sc))
 
     def vector(self, name: str) -> np.ndarray:
         n = lib().pdlp_oracle_get_vector(self.h, name.encode(), None)
