@@ -704,6 +704,8 @@ cuopt_int_t cuOptB200SolverProfileKernels(cuOptB200Solver solver,
     profile->grid_primal          = k.grid_primal;
     profile->grid_dual            = k.grid_dual;
     profile->grid_transpose       = k.grid_transpose;
+    profile->ms_transpose_partial      = k.ms_transpose_partial;
+    profile->ms_transpose_partial_wide = k.ms_transpose_partial_wide;
   });
   return CUOPT_SUCCESS;
 }

@@ -39,7 +39,101 @@ __global__ void k_permute(int nnz, const int* __restrict__ sorted_entry, const i
   }
 }
 
+// ---- column-block split (gather blocking) ----
+constexpr int MAX_COLUMN_BLOCKS = 16;
+struct block_ptrs_t {
+  int* off[MAX_COLUMN_BLOCKS];
+  int* idx[MAX_COLUMN_BLOCKS];
+  double* val[MAX_COLUMN_BLOCKS];
+};
+// counts[b * (rows + 1) + r] = entries of row r whose column lies in block b (slot rows stays 0: scan total)
+__global__ void k_block_count(int rows, const int* __restrict__ off, const int* __restrict__ idx, int width, int n_blocks,
+                              int* __restrict__ counts)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
+    int c[MAX_COLUMN_BLOCKS];
+#pragma unroll
+    for (int b = 0; b < MAX_COLUMN_BLOCKS; ++b) c[b] = 0;
+    for (int p = off[r]; p < off[r + 1]; ++p) {
+      const int b = idx[p] / width;
+#pragma unroll
+      for (int q = 0; q < MAX_COLUMN_BLOCKS; ++q)
+        if (q == b) ++c[q];
+    }
+#pragma unroll
+    for (int b = 0; b < MAX_COLUMN_BLOCKS; ++b)
+      if (b < n_blocks) counts[(size_t)b * (rows + 1) + r] = c[b];
+  }
+}
+// stable: the entries of a row keep their order inside each block
+__global__ void k_block_fill(int rows, const int* __restrict__ off, const int* __restrict__ idx,
+                             const double* __restrict__ val, int width, block_ptrs_t out)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
+    int pos[MAX_COLUMN_BLOCKS];
+#pragma unroll
+    for (int b = 0; b < MAX_COLUMN_BLOCKS; ++b) pos[b] = out.off[b] ? out.off[b][r] : 0;
+    for (int p = off[r]; p < off[r + 1]; ++p) {
+      const int j = idx[p], b = j / width;
+      const double v = val[p];
+#pragma unroll
+      for (int q = 0; q < MAX_COLUMN_BLOCKS; ++q)
+        if (q == b) {
+          out.idx[q][pos[q]] = j;
+          out.val[q][pos[q]] = v;
+          ++pos[q];
+        }
+    }
+  }
+}
+
 }  // namespace
+
+// Splits a CSR matrix into n_blocks CSR matrices with the same rows: block b keeps the entries whose column lies in
+// [b * width, (b + 1) * width), in their original order, with GLOBAL column indices.  Step 1 (this call) fills the
+// row offsets blk_off[b] (rows + 1 ints each, caller-allocated) and returns the block sizes; the caller allocates
+// idx / val and calls csr_split_columns_fill.
+void csr_split_columns_offsets(int rows, const int* off, const int* idx, int width, int n_blocks, int* const* blk_off,
+                               int* blk_nnz_host, cudaStream_t stream)
+{
+  if (n_blocks > MAX_COLUMN_BLOCKS) throw lp_error(error_type_t::RuntimeError, "too many column blocks");
+  dvec<int> counts((size_t)n_blocks * (rows + 1));
+  counts.zero(stream);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = std::max(1, std::min((rows + 255) / 256, sms * 8));
+  k_block_count<<<grid, 256, 0, stream>>>(rows, off, idx, width, n_blocks, counts.data());
+  CUOPT_CUDA_TRY(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  CUOPT_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.data(), blk_off[0], rows + 1, stream));
+  dvec<unsigned char> tmp(tmp_bytes + 16);
+  for (int b = 0; b < n_blocks; ++b) {
+    size_t bytes = tmp.size();
+    CUOPT_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.data(), bytes, counts.data() + (size_t)b * (rows + 1), blk_off[b],
+                                                  rows + 1, stream));
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(blk_nnz_host + b, blk_off[b] + rows, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  }
+  CUOPT_CUDA_TRY(cudaStreamSynchronize(stream));
+}
+
+void csr_split_columns_fill(int rows, const int* off, const int* idx, const double* val, int width, int n_blocks,
+                            int* const* blk_off, int* const* blk_idx, double* const* blk_val, cudaStream_t stream)
+{
+  block_ptrs_t out{};
+  for (int b = 0; b < n_blocks; ++b) {
+    out.off[b] = blk_off[b];
+    out.idx[b] = blk_idx[b];
+    out.val[b] = blk_val[b];
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = std::max(1, std::min((rows + 255) / 256, sms * 8));
+  k_block_fill<<<grid, 256, 0, stream>>>(rows, off, idx, val, width, out);
+  CUOPT_CUDA_TRY(cudaGetLastError());
+  CUOPT_CUDA_TRY(cudaStreamSynchronize(stream));
+}
 
 // toff must hold cols + 1 ints, tidx / tval nnz elements.  All pointers are device pointers.
 void csr_transpose_device(int rows, int cols, int nnz, const int* off, const int* idx, const double* val, int* toff,

@@ -120,6 +120,36 @@ __device__ __forceinline__ double block_reduce(double v, double* scratch)
   return r;
 }
 
+// L2 residency hints (createpolicy + ld/st ...L2::cache_hint).  At configs[3] sizes the vector an SpMV gathers from is
+// 80 MB: it only stays in the 126 MB L2 if the ~2 GB of read-once streams passing by are marked evict-first and
+// the vector itself evict-last.  `keep` marks the gathered vector (its producer's stores and the gathers), `stream`
+// everything that is touched once per kernel.  Mode 0 (CUOPT_B200_L2_HINTS=0) makes both policies evict-normal.
+struct l2_policy_t {
+  unsigned long long keep, stream;
+};
+__device__ __forceinline__ l2_policy_t make_l2_policies(int mode)
+{
+  l2_policy_t p;
+  if (mode) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+  } else {
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p.keep));
+    p.stream = p.keep;
+  }
+  return p;
+}
+__device__ __forceinline__ double ld_l2(const double* p, unsigned long long policy)
+{
+  double v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void st_l2(double* p, double v, unsigned long long policy)
+{
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy) : "memory");
+}
+
 // Streaming (read-once) loads: keep them from displacing the gathered vector in L1/L2.
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }

@@ -31,6 +31,7 @@ namespace cuopt_b200 {
 constexpr int EW_THREADS  = 256;  // element-wise kernels
 constexpr int PDHG_MIN_CTAS = 6;  // hot SpMV kernels: <= 40 registers, 6 x 256 threads per SM (measured optimum)
 constexpr int EVAL_STAGES = 3;    // two-vector evaluation kernels
+static __device__ int g_l2_hints = 1;  // device_utils.cuh make_l2_policies; CUOPT_B200_L2_HINTS=0 clears it (measured: profiles/r1/l2_hints_experiment.txt)
 
 // Device-resident control block: every scalar the PDHG loop reads or writes.
 struct pdhg_ctl_t {
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_primal_step(const pdhg_ctl_t* __
   const bool pending      = ctl->pending_avg != 0;
   const double w          = ctl->pending_weight;
   const int stride        = gridDim.x * blockDim.x;
+  const l2_policy_t pol   = make_l2_policies(g_l2_hints);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
     const double xj = x[j];
     if (pending) sum_x[j] = sum_x[j] + w * xj;
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_primal_step(const pdhg_ctl_t* __
     double next           = xj - (tau * gradient);
     next                  = fmax(fmin(next, ld_stream(u + j)), ld_stream(l + j));
     xn[j]                 = next;
-    xbar[j]               = next - xj + next;
+    st_l2(xbar + j, next - xj + next, pol.keep);  // K2 gathers from xbar: keep it in L2
   }
 }
 
@@ -259,6 +261,7 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_dual_step(const
   const bool pending = ctl->pending_avg != 0;
   const double w     = ctl->pending_weight;
   double dy2         = 0.0;
+  const l2_policy_t pol = make_l2_policies(g_l2_hints);
   struct payload_t {
     double y, lc, uc, sum;
   };
@@ -276,11 +279,11 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_dual_step(const
     const double low = next + sigma * p.lc;
     const double up  = next + sigma * p.uc;
     next             = fmax(low, fmin(up, 0.0));
-    yn[i]            = next;
+    st_l2(yn + i, next, pol.keep);  // K3 gathers from y': keep it in L2
     const double d   = next - p.y;
     dy2 += d * d;
   };
-  spmv_warp_rows<payload_t>(A, xbar, prod[threadIdx.x >> 5], pre_op, row_op);
+  spmv_warp_rows<payload_t>(A, xbar, prod[threadIdx.x >> 5], pre_op, row_op, pol.keep);
   const double tot = block_reduce(dy2, red);
   if (threadIdx.x == 0) part_dy2[blockIdx.x] = tot;
 }
@@ -312,21 +315,22 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_step(
   const double* aty = cur ? aty1 : aty0;
   double* atyn      = cur ? aty0 : aty1;
   double acc[2]     = {0.0, 0.0};  // interaction, ||dx||^2
+  const l2_policy_t pol = make_l2_policies(g_l2_hints);
   struct payload_t {
     double dx, aty;
   };
   auto pre_op = [&](int j) {
     payload_t p;
-    p.dx  = xn[j] - x[j];
-    p.aty = aty[j];
+    p.dx  = ld_l2(xn + j, pol.stream) - ld_l2(x + j, pol.stream);
+    p.aty = ld_l2(aty + j, pol.stream);
     return p;
   };
   auto row_op = [&](int j, double s, const payload_t& p) {
-    atyn[j] = s;
+    st_l2(atyn + j, s, pol.stream);
     acc[0] += p.dx * (s - p.aty);
     acc[1] += p.dx * p.dx;
   };
-  spmv_warp_rows<payload_t>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op);
+  spmv_warp_rows<payload_t>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op, pol.keep);
 
   if (!publish_and_elect<2>(acc, parts, &ctl->ticket[0], red)) return;
   const double interaction = gather_partials(parts, gridDim.x, red);
@@ -342,7 +346,8 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_step(
 // A^T y' that is summed over ranks (NCCL all-reduce on the solver stream) between K3a and K3b.  The extra slot
 // buf[n] carries this rank's ||dy||^2 through the same collective.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_partial(const pdhg_ctl_t* __restrict__ ctl,
+template <int RPL>
+__global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? PDHG_MIN_CTAS : 4) k_transpose_partial(const pdhg_ctl_t* __restrict__ ctl,
                                                                                    csr_warp_view_t AT,
                                                                                    const double* __restrict__ ybuf0,
                                                                                    const double* __restrict__ ybuf1,
@@ -354,7 +359,7 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_parti
   struct payload_t {};
   auto pre_op = [&](int) { return payload_t{}; };
   auto row_op = [&](int j, double s, const payload_t&) { buf[j] = s; };
-  spmv_warp_rows<payload_t>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op);
+  spmv_warp_rows<payload_t, RPL>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op, make_l2_policies(g_l2_hints).keep);
 }
 // buf[slot] = sum of `count` per-CTA partials (one CTA, fixed order)
 __global__ void __launch_bounds__(EW_THREADS) k_sum_partials(const pdhg_ctl_t* __restrict__ ctl,
@@ -463,7 +468,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_primal_step_bcast(pdhg_ctl_t* __
 
 // K3p with the reduce-scatter fused in: column j's partial goes straight to its owner's staging row of this rank;
 // stage_peers.p[h] = rank h's stage + rank * nslice.
-__global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_partial_scatter(pdhg_ctl_t* __restrict__ ctl,
+template <int RPL>
+__global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? PDHG_MIN_CTAS : 4) k_transpose_partial_scatter(pdhg_ctl_t* __restrict__ ctl,
                                                                                            csr_warp_view_t AT,
                                                                                            const double* __restrict__ ybuf0,
                                                                                            const double* __restrict__ ybuf1,
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_parti
       if (h == r) base = stage_peers.p[r];
     base[j - h * nslice] = s;
   };
-  spmv_warp_rows<payload_t>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op);
+  spmv_warp_rows<payload_t, RPL>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op, make_l2_policies(g_l2_hints).keep);
   peer_signal_grid_done(&ctl->ticket[2], flags, world, DIST_FLAG_PARTIAL + rank, epoch);
 }
 
@@ -568,6 +574,143 @@ __global__ void k_step_rule_gather(pdhg_ctl_t* __restrict__ ctl, const double* _
   pdhg_step_rule(ctl, interaction, dx2, dy2);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Gather blocking (large LPs).  When the vector an SpMV gathers from is much larger than what stays in L2 (80 MB at
+// configs[3] against a 126 MB L2 that also sees ~2 GB of streams per kernel), ncu shows the fused kernels DRAM-bound
+// at 2.4x their algorithmic bytes: every gathered double drags a 32-byte sector in from HBM (profiles/r1).  The
+// host then splits the matrix by COLUMN blocks whose slice of the gathered vector is L2-sized (csr_transpose.cu),
+// and K2 / K3 become   B x k_block_pass (t += A_b * x, payload-free, wide warp blocks)  +  one element-wise epilogue
+// (the row_op of the fused kernel).  Rows keep their entry order inside and across blocks and every pass continues
+// the row's running sum, so t is the same left-to-right sum the fused kernel forms.
+// ---------------------------------------------------------------------------------------------
+// t[r] = (first ? 0 : t[r]) + sum over the entries of row r in this column block.
+//   pick_candidate = 0: x = x0;  1: x = the candidate dual y' = parity ? x0 : x1  (K3).
+//   wait_flags: peer transport only, first pass of K2 (the xbar slices of the other ranks must have landed).
+template <int RPL>
+__global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? PDHG_MIN_CTAS : 4) k_block_pass(const pdhg_ctl_t* __restrict__ ctl,
+                                                                                          csr_warp_view_t Ab,
+                                                                                          const double* __restrict__ x0,
+                                                                                          const double* __restrict__ x1,
+                                                                                          int pick_candidate,
+                                                                                          double* __restrict__ t,
+                                                                                          int first,
+                                                                                          const unsigned long long* wait_flags,
+                                                                                          int n_wait)
+{
+  if (!ctl->active) return;
+  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
+  if (wait_flags) peer_wait(wait_flags, n_wait, (unsigned long long)ctl->attempts + 1ull);
+  const double* x       = pick_candidate ? (ctl->parity ? x0 : x1) : x0;
+  const l2_policy_t pol = make_l2_policies(g_l2_hints);
+  struct payload_t {
+    double init;
+  };
+  auto pre_op = [&](int r) {
+    payload_t p;
+    p.init = first ? 0.0 : ld_l2(t + r, pol.stream);
+    return p;
+  };
+  auto row_op = [&](int r, double s, const payload_t&) { st_l2(t + r, s, pol.stream); };
+  spmv_warp_rows<payload_t, RPL, true>(Ab, x, prod[threadIdx.x >> 5], pre_op, row_op, pol.keep);
+}
+
+// K2 epilogue on t = A * xbar (the row_op of k_dual_step, element-wise).
+__global__ void __launch_bounds__(EW_THREADS) k_dual_epilogue(const pdhg_ctl_t* __restrict__ ctl,
+                                                              int m,
+                                                              const double* __restrict__ t,
+                                                              double* __restrict__ ybuf0,
+                                                              double* __restrict__ ybuf1,
+                                                              const double* __restrict__ lc,
+                                                              const double* __restrict__ uc,
+                                                              double* __restrict__ sum_y,
+                                                              double* __restrict__ part_dy2)
+{
+  if (!ctl->active) return;
+  __shared__ double red[32];
+  const int cur         = ctl->parity;
+  const double* y       = cur ? ybuf1 : ybuf0;
+  double* yn            = cur ? ybuf0 : ybuf1;
+  const double sigma    = ctl->sigma;
+  const bool pending    = ctl->pending_avg != 0;
+  const double w        = ctl->pending_weight;
+  const l2_policy_t pol = make_l2_policies(g_l2_hints);
+  double dy2            = 0.0;
+  const int stride      = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const double yi = y[i];
+    if (pending) sum_y[i] = sum_y[i] + w * yi;
+    double next      = yi - (sigma * ld_l2(t + i, pol.stream));
+    const double low = next + sigma * ld_stream(lc + i);
+    const double up  = next + sigma * ld_stream(uc + i);
+    next             = fmax(low, fmin(up, 0.0));
+    st_l2(yn + i, next, pol.keep);
+    const double d = next - yi;
+    dy2 += d * d;
+  }
+  const double tot = block_reduce(dy2, red);
+  if (threadIdx.x == 0) part_dy2[blockIdx.x] = tot;
+}
+
+// K3 epilogue on t = A^T * y' (the row_op of k_transpose_step + the step rule in the last CTA).
+__global__ void __launch_bounds__(EW_THREADS) k_transpose_epilogue(pdhg_ctl_t* __restrict__ ctl,
+                                                                   int n,
+                                                                   const double* __restrict__ t,
+                                                                   const double* __restrict__ xbuf0,
+                                                                   const double* __restrict__ xbuf1,
+                                                                   double* __restrict__ aty0,
+                                                                   double* __restrict__ aty1,
+                                                                   double* __restrict__ parts,
+                                                                   const double* __restrict__ part_dy2,
+                                                                   int n_part_dy2)
+{
+  if (!ctl->active) return;
+  __shared__ double red[32];
+  const int cur     = ctl->parity;
+  const double* x   = cur ? xbuf1 : xbuf0;
+  const double* xn  = cur ? xbuf0 : xbuf1;
+  const double* aty = cur ? aty1 : aty0;
+  double* atyn      = cur ? aty0 : aty1;
+  double acc[2]     = {0.0, 0.0};
+  const int stride  = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double s = __ldcs(t + j);
+    atyn[j]        = s;
+    const double d = xn[j] - x[j];
+    acc[0] += d * (s - aty[j]);
+    acc[1] += d * d;
+  }
+  if (!publish_and_elect<2>(acc, parts, &ctl->ticket[0], red)) return;
+  const double interaction = gather_partials(parts, gridDim.x, red);
+  const double dx2         = gather_partials(parts + gridDim.x, gridDim.x, red);
+  const double dy2         = gather_partials(part_dy2, n_part_dy2, red);
+  if (threadIdx.x != 0) return;
+  pdhg_step_rule(ctl, interaction, dx2, dy2);
+}
+
+// Peer transport, blocked K3p: t = partial A_g^T y'_g over all n columns -> staging rows of the slice owners.
+__global__ void __launch_bounds__(EW_THREADS) k_scatter_partials(pdhg_ctl_t* __restrict__ ctl,
+                                                                 int n,
+                                                                 const double* __restrict__ t,
+                                                                 peer_ptrs_t stage_peers,
+                                                                 int nslice,
+                                                                 peer_flags_t flags,
+                                                                 int world,
+                                                                 int rank)
+{
+  if (!ctl->active) return;
+  const unsigned long long epoch = (unsigned long long)ctl->attempts + 1ull;
+  const int stride               = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const int h  = j / nslice;
+    double* base = stage_peers.p[0];
+#pragma unroll
+    for (int r = 1; r < DIST_MAX_PEERS; ++r)
+      if (h == r) base = stage_peers.p[r];
+    base[j - h * nslice] = __ldcs(t + j);
+  }
+  peer_signal_grid_done(&ctl->ticket[2], flags, world, DIST_FLAG_PARTIAL + rank, epoch);
+}
+
 // Applies a still-pending running-average update (end of a batch, before averages are formed).
 __global__ void __launch_bounds__(EW_THREADS) k_flush_average(const pdhg_ctl_t* __restrict__ ctl,
                                                               int n,
@@ -596,7 +739,8 @@ __global__ void k_begin_batch(pdhg_ctl_t* ctl, int steps)
 }
 
 // Plain y = A x on the row-block scheme (A^T y after a restart to the average, pdhg.cu:120-134).
-__global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_spmv(csr_warp_view_t A,
+template <int RPL>
+__global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? PDHG_MIN_CTAS : 4) k_spmv(csr_warp_view_t A,
                                                                       const double* __restrict__ x,
                                                                       double* __restrict__ out)
 {
@@ -604,7 +748,7 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_spmv(csr_warp_v
   struct payload_t {};
   auto pre_op = [&](int) { return payload_t{}; };
   auto row_op = [&](int i, double s, const payload_t&) { out[i] = s; };
-  spmv_warp_rows<payload_t>(A, x, prod[threadIdx.x >> 5], pre_op, row_op);
+  spmv_warp_rows<payload_t, RPL>(A, x, prod[threadIdx.x >> 5], pre_op, row_op, make_l2_policies(g_l2_hints).keep);
 }
 
 // =============================================================================================

@@ -31,11 +31,18 @@ namespace cuopt_b200 {
 namespace {
 
 struct csr_dev_t {
-  int rows = 0, cols = 0, nnz = 0, n_blocks = 0, n_wb = 0;
+  int rows = 0, cols = 0, nnz = 0, n_blocks = 0, n_wb = 0, n_wb_wide = 0;
   dvec<int> off, idx;
   dvec<double> val;
   dvec<int4> blk;    // CTA row blocks (TMA pipeline of the evaluation kernels)
   dvec<int2> wdesc;  // warp row blocks (hot PDHG kernels)
+  dvec<int2> wdesc_wide;  // <= 256 rows per block, only cut for very sparse matrices (spmv_warp.cuh, RPL = 8)
+  bool wide() const { return n_wb_wide > 0; }
+  csr_warp_view_t warp_view_wide() const
+  {
+    return csr_warp_view_t{off_ptr(), idx_ptr(), val.data(), n_wb_wide,
+                           structure ? structure->wdesc_wide.data() : wdesc_wide.data()};
+  }
   const csr_dev_t* structure = nullptr;  // scaled copies share offsets / indices / row blocks with the original
   const int* off_ptr() const { return structure ? structure->off.data() : off.data(); }
   const int* idx_ptr() const { return structure ? structure->idx.data() : idx.data(); }
@@ -48,7 +55,7 @@ struct csr_dev_t {
   // same sparsity pattern, own values (device-to-device copy)
   void alias_structure_copy_values(const csr_dev_t& o, cudaStream_t s)
   {
-    rows = o.rows; cols = o.cols; nnz = o.nnz; n_blocks = o.n_blocks; n_wb = o.n_wb;
+    rows = o.rows; cols = o.cols; nnz = o.nnz; n_blocks = o.n_blocks; n_wb = o.n_wb; n_wb_wide = o.n_wb_wide;
     structure = &o;
     val.copy_from(o.val, s);
   }
@@ -74,9 +81,10 @@ std::vector<int4> build_row_blocks(const std::vector<int>& off)
   return blocks;
 }
 
-// Warp row blocks for the hot kernels: consecutive rows with <= WARP_NNZ nonzeros and <= 32 rows; a longer row is a
-// block of its own.  Returns n_wb + 1 descriptors {first row, first nnz}.
-std::vector<int2> build_warp_blocks(const std::vector<int>& off)
+// Warp row blocks for the hot kernels: consecutive rows with <= WARP_NNZ nonzeros and <= max_rows rows (32, or
+// 32 * WARP_WIDE_RPL for the wide schedule); a longer row is a block of its own.  Returns n_wb + 1 descriptors
+// {first row, first nnz}.
+std::vector<int2> build_warp_blocks(const std::vector<int>& off, int max_rows = 32)
 {
   std::vector<int2> wd;
   const int rows = (int)off.size() - 1;
@@ -87,7 +95,7 @@ std::vector<int2> build_warp_blocks(const std::vector<int>& off)
     if (off[r + 1] - lo > WARP_NNZ) {
       r1 = r + 1;
     } else {
-      while (r1 < rows && off[r1 + 1] - lo <= WARP_NNZ && (r1 - r) < 32) ++r1;
+      while (r1 < rows && off[r1 + 1] - lo <= WARP_NNZ && (r1 - r) < max_rows) ++r1;
     }
     wd.push_back(make_int2(r, lo));
     r = r1;
@@ -97,14 +105,29 @@ std::vector<int2> build_warp_blocks(const std::vector<int>& off)
 }
 
 // Row-block / warp-block schedules from HOST row offsets.
+void upload_warp_schedules(csr_dev_t& d, const std::vector<int>& off, cudaStream_t s);
+
 void upload_schedules(csr_dev_t& d, const std::vector<int>& off, cudaStream_t s)
 {
   auto blocks = build_row_blocks(off);
   d.n_blocks  = (int)blocks.size();
   d.blk.upload(blocks, s);
+  upload_warp_schedules(d, off, s);
+}
+
+// warp blocks only (column blocks of the gather blocking never run the CTA-level evaluation kernels)
+void upload_warp_schedules(csr_dev_t& d, const std::vector<int>& off, cudaStream_t s)
+{
   auto wblocks = build_warp_blocks(off);
   d.n_wb       = (int)wblocks.size() - 1;
   d.wdesc.upload(wblocks, s);
+  const long long rows = (long long)off.size() - 1;
+  d.n_wb_wide          = 0;
+  if (rows > 0 && (long long)off[rows] <= 4 * rows) {  // <= 4 nonzeros per row on average
+    auto wide   = build_warp_blocks(off, 32 * WARP_WIDE_RPL);
+    d.n_wb_wide = (int)wide.size() - 1;
+    d.wdesc_wide.upload(wide, s);
+  }
 }
 
 void upload_csr(csr_dev_t& d, int rows, int cols, const std::vector<int>& off, const std::vector<int>& idx,
@@ -123,6 +146,11 @@ void upload_csr(csr_dev_t& d, int rows, int cols, const std::vector<int>& off, c
 
 void csr_transpose_device(int rows, int cols, int nnz, const int* off, const int* idx, const double* val, int* toff,
                           int* tidx, double* tval, cudaStream_t stream);  // csr_transpose.cu
+
+void csr_split_columns_offsets(int rows, const int* off, const int* idx, int width, int n_blocks, int* const* blk_off,
+                               int* blk_nnz_host, cudaStream_t stream);  // csr_transpose.cu
+void csr_split_columns_fill(int rows, const int* off, const int* idx, const double* val, int width, int n_blocks,
+                            int* const* blk_off, int* const* blk_idx, double* const* blk_val, cudaStream_t stream);
 
 namespace {
 
@@ -192,7 +220,19 @@ struct pdlp_solver_t::impl_t {
   pdhg_ctl_t* h_ctl = nullptr;  // pinned mirrors
   eval_t* h_eval    = nullptr;
   double* h_scalar  = nullptr;
-  int grid_sp = 1;
+  int grid_sp = 1, grid_sp_wide = 1, grid_k3p_wide = 1;
+  // gather blocking (pdlp_kernels.cuh): the scaled A / A^T cut into column blocks whose slice of the gathered vector
+  // is L2-sized; B == 1 (small LPs) keeps the fused kernels
+  struct gather_blocks_t {
+    int B = 1, width = 0;
+    std::vector<csr_dev_t> blk;
+    std::vector<int> grid;  // per block, for the schedule (wide or not) its pass uses
+    bool on() const { return B > 1; }
+  };
+  gather_blocks_t blkA, blkAT;
+  dvec<double> t_m, t_n;
+  size_t gather_block_bytes = 32u << 20;
+  int n_part_dy2 = 1;  // CTAs that publish ||dy||^2 partials: grid_k2 (fused K2) or grid_m (blocked K2 epilogue)
   int grid_k1 = 1, grid_k2 = 1, grid_k3 = 1, grid_er = 1, grid_ec = 1, grid_n = 1, grid_m = 1, grid_misc = 1;
   std::map<int, cudaGraphExec_t> graphs;
   bool use_graphs = true;
@@ -267,6 +307,10 @@ struct pdlp_solver_t::impl_t {
     CUOPT_CUDA_TRY(cudaMallocHost(&h_eval, 2 * sizeof(eval_t)));
     CUOPT_CUDA_TRY(cudaMallocHost(&h_scalar, 8 * sizeof(double)));
     if (const char* e = std::getenv("CUOPT_B200_NO_GRAPH")) use_graphs = !(e[0] == '1');
+    if (const char* e = std::getenv("CUOPT_B200_L2_HINTS")) {  // experiment switch, default on (pdlp_kernels.cuh)
+      const int on = e[0] != '0';
+      CUOPT_CUDA_TRY(cudaMemcpyToSymbol(g_l2_hints, &on, sizeof(int)));
+    }
 
     // problem_t construction semantics (mip/problem/problem.cu:55-93, problem_helpers.cuh:34-142)
     std::vector<double> hc = p.objective_coefficients, hl, hu, hlc, huc;
@@ -326,14 +370,21 @@ struct pdlp_solver_t::impl_t {
     };
     grid_k2   = warp_grid((const void*)k_dual_step, As.n_wb);
     grid_k3   = warp_grid((const void*)k_transpose_step, ATs.n_wb);
-    grid_sp   = warp_grid((const void*)k_spmv, ATs.n_wb);
+    grid_sp   = warp_grid((const void*)k_spmv<1>, ATs.n_wb);
+    if (ATs.wide()) {
+      grid_sp_wide  = warp_grid((const void*)k_spmv<WARP_WIDE_RPL>, ATs.n_wb_wide);
+      grid_k3p_wide = warp_grid((const void*)k_transpose_partial<WARP_WIDE_RPL>, ATs.n_wb_wide);
+    }
     grid_er   = occ_grid((const void*)k_eval_rows, A.n_blocks, SMEM_EVAL);
     grid_ec   = occ_grid((const void*)k_eval_cols, AT.n_blocks, SMEM_EVAL);
     grid_n    = ew_grid(n, sms);
     grid_m    = ew_grid(m, sms);
     grid_k1   = grid_n;
     grid_misc = ew_grid(std::max(n, m), sms);
-    part_dy2.resize(grid_k2);
+    part_dy2.resize(std::max(grid_k2, grid_m));
+    n_part_dy2 = grid_k2;
+    // size of the slice of the gathered vector one column block may span (0 = never block); bytes, for the tests too
+    if (const char* e = std::getenv("CUOPT_B200_GATHER_BLOCK_BYTES")) gather_block_bytes = (size_t)std::atoll(e);
     part_k3.resize(2 * (size_t)std::max(grid_k3, grid_n));
     part_rows.resize(6 * (size_t)grid_er);
     part_cols.resize(8 * (size_t)std::max(grid_ec, grid_n));
@@ -478,6 +529,9 @@ struct pdlp_solver_t::impl_t {
     if (hp.compute_initial_step_size_before_scaling) step = initial_step_size(A);
     if (hp.compute_initial_primal_weight_before_scaling) weight = initial_primal_weight(c, lc, uc);
     scale_problem();
+    build_gather_blocks(As, blkA, t_m);
+    build_gather_blocks(ATs, blkAT, t_n);
+    n_part_dy2 = blkA.on() ? grid_m : grid_k2;
     if (!hp.compute_initial_step_size_before_scaling) step = initial_step_size(As);
     if (!hp.compute_initial_primal_weight_before_scaling) weight = initial_primal_weight(cs, lcs, ucs);
 
@@ -584,6 +638,125 @@ struct pdlp_solver_t::impl_t {
   }
 
   // ------------------------------------------------------------------------------ PDHG batches
+  // Cuts the scaled matrix M into column blocks (device, stable) when the vector it gathers from exceeds the block size.
+  void build_gather_blocks(const csr_dev_t& M, gather_blocks_t& g, dvec<double>& t)
+  {
+    g = gather_blocks_t{};
+    const size_t bytes = (size_t)M.cols * sizeof(double);
+    if (gather_block_bytes == 0 || bytes <= gather_block_bytes + gather_block_bytes / 2 || M.nnz == 0) return;
+    int B     = (int)std::min<size_t>(16, (bytes + gather_block_bytes - 1) / gather_block_bytes);
+    g.width   = (((M.cols + B - 1) / B) + 31) & ~31;
+    B         = (M.cols + g.width - 1) / g.width;
+    if (B <= 1) return;
+    g.B = B;
+    g.blk.resize(B);
+    std::vector<int*> offs(B), idxs(B);
+    std::vector<double*> vals(B);
+    std::vector<int> nnz_b(B, 0);
+    for (int b = 0; b < B; ++b) {
+      g.blk[b].rows = M.rows;
+      g.blk[b].cols = M.cols;
+      g.blk[b].off.resize((size_t)M.rows + 1, SPMV_TAIL_SLACK);
+      offs[b] = g.blk[b].off.data();
+    }
+    csr_split_columns_offsets(M.rows, M.off_ptr(), M.idx_ptr(), g.width, B, offs.data(), nnz_b.data(), stream);
+    for (int b = 0; b < B; ++b) {
+      g.blk[b].nnz = nnz_b[b];
+      g.blk[b].idx.resize((size_t)nnz_b[b], SPMV_TAIL_SLACK);
+      g.blk[b].val.resize((size_t)nnz_b[b], SPMV_TAIL_SLACK);
+      idxs[b] = g.blk[b].idx.data();
+      vals[b] = g.blk[b].val.data();
+    }
+    csr_split_columns_fill(M.rows, M.off_ptr(), M.idx_ptr(), M.val.data(), g.width, B, offs.data(), idxs.data(), vals.data(),
+                           stream);
+    std::vector<int> hoff((size_t)M.rows + 1);
+    g.grid.resize(B);
+    auto grid_for = [&](const void* kernel, int n_wb) {
+      int per_sm = 1;
+      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARP_THREADS, 0));
+      return std::max(1, std::min((n_wb + WARP_PER_CTA - 1) / WARP_PER_CTA, sms * std::max(per_sm, 1)));
+    };
+    for (int b = 0; b < B; ++b) {
+      g.blk[b].off.download(hoff.data(), stream);
+      sync();
+      upload_warp_schedules(g.blk[b], hoff, stream);
+      g.grid[b] = g.blk[b].wide() ? grid_for((const void*)k_block_pass<WARP_WIDE_RPL>, g.blk[b].n_wb_wide)
+                                  : grid_for((const void*)k_block_pass<1>, g.blk[b].n_wb);
+    }
+    t.resize((size_t)M.rows);
+    t.zero(stream);
+  }
+  // t (+)= M_b * x for every column block, in block order
+  void launch_block_passes(const gather_blocks_t& g, const double* x0, const double* x1, int pick_candidate, double* t,
+                           const unsigned long long* wait_flags, int n_wait)
+  {
+    for (int b = 0; b < g.B; ++b) {
+      const csr_dev_t& M = g.blk[b];
+      const unsigned long long* wf = b == 0 ? wait_flags : nullptr;
+      if (M.wide())
+        k_block_pass<WARP_WIDE_RPL><<<g.grid[b], WARP_THREADS, 0, stream>>>(d_ctl.data(), M.warp_view_wide(), x0, x1,
+                                                                            pick_candidate, t, b == 0, wf, n_wait);
+      else
+        k_block_pass<1><<<g.grid[b], WARP_THREADS, 0, stream>>>(d_ctl.data(), M.warp_view(), x0, x1, pick_candidate, t,
+                                                                b == 0, wf, n_wait);
+    }
+  }
+  // K2: fused, or column-blocked passes + element-wise epilogue.  wait_flags: peer transport (xbar slices of the peers)
+  void enqueue_k2(const unsigned long long* wait_flags, int n_wait)
+  {
+    if (!blkA.on()) {
+      k_dual_step<<<grid_k2, WARP_THREADS, 0, stream>>>(d_ctl.data(), As.warp_view(), xbar.data(), ybuf[0].data(),
+                                                        ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(), part_dy2.data(),
+                                                        wait_flags, n_wait);
+      return;
+    }
+    launch_block_passes(blkA, xbar.data(), xbar.data(), 0, t_m.data(), wait_flags, n_wait);
+    k_dual_epilogue<<<grid_m, EW_THREADS, 0, stream>>>(d_ctl.data(), m, t_m.data(), ybuf[0].data(), ybuf[1].data(), lcs.data(),
+                                                       ucs.data(), sum_y.data(), part_dy2.data());
+  }
+  // K3 on one GPU: fused, or column-blocked passes + element-wise epilogue with the step rule
+  void enqueue_k3()
+  {
+    if (!blkAT.on()) {
+      k_transpose_step<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
+                                                             xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
+                                                             atybuf[1].data(), part_k3.data(), part_dy2.data(), n_part_dy2);
+      return;
+    }
+    launch_block_passes(blkAT, ybuf[0].data(), ybuf[1].data(), 1, t_n.data(), nullptr, 0);
+    k_transpose_epilogue<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, t_n.data(), xbuf[0].data(), xbuf[1].data(),
+                                                            atybuf[0].data(), atybuf[1].data(), part_k3.data(),
+                                                            part_dy2.data(), n_part_dy2);
+  }
+  int kernels_per_attempt() const
+  {
+    const int k2 = blkA.on() ? blkA.B + 1 : 1;
+    if (!sharded()) return 1 + k2 + (blkAT.on() ? blkAT.B + 1 : 1);
+    const int k3p = blkAT.on() ? blkAT.B + (dist_mode == DIST_P2P ? 1 : 0) : 1;
+    return 1 + k2 + k3p + (dist_mode == DIST_ALLREDUCE ? 2 : 2);
+  }
+
+  // partial A_g^T y' of this rank into dist_buf (NCCL transports); wide blocks when the shard's transpose is very sparse
+  void launch_transpose_partial()
+  {
+    if (blkAT.on()) {  // the passes accumulate straight into the collective's send buffer
+      launch_block_passes(blkAT, ybuf[0].data(), ybuf[1].data(), 1, dist_buf.data(), nullptr, 0);
+      return;
+    }
+    if (ATs.wide())
+      k_transpose_partial<WARP_WIDE_RPL><<<grid_k3p_wide, WARP_THREADS, 0, stream>>>(
+        d_ctl.data(), ATs.warp_view_wide(), ybuf[0].data(), ybuf[1].data(), dist_buf.data());
+    else
+      k_transpose_partial<1><<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(),
+                                                                   ybuf[1].data(), dist_buf.data());
+  }
+  // out = M v on the warp-block scheme
+  void launch_spmv(const csr_dev_t& M, const double* v, double* out)
+  {
+    if (M.wide()) k_spmv<WARP_WIDE_RPL><<<grid_sp_wide, WARP_THREADS, 0, stream>>>(M.warp_view_wide(), v, out);
+    else k_spmv<1><<<grid_sp, WARP_THREADS, 0, stream>>>(M.warp_view(), v, out);
+  }
+
   // scheme (ii): this rank updates only its slice of the primal side (kernel comments in pdlp_kernels.cuh)
   void enqueue_sliced_attempt()
   {
@@ -593,13 +766,18 @@ struct pdlp_solver_t::impl_t {
       k_primal_step_bcast<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, x0, x1, a0, a1, cs.data() + j0,
                                                                  ls.data() + j0, us.data() + j0, sum_x.data() + j0, p_xbar,
                                                                  p_flags, G, rk);
-      k_dual_step<<<grid_k2, WARP_THREADS, 0, stream>>>(d_ctl.data(), As.warp_view(), xbar.data(), ybuf[0].data(),
-                                                        ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(), part_dy2.data(),
-                                                        d_flags.data() + DIST_FLAG_XBAR, G);
-      k_transpose_partial_scatter<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(),
-                                                                        ybuf[1].data(), p_stage, nslice, p_flags, G, rk);
+      enqueue_k2(d_flags.data() + DIST_FLAG_XBAR, G);
+      if (blkAT.on()) {
+        launch_block_passes(blkAT, ybuf[0].data(), ybuf[1].data(), 1, t_n.data(), nullptr, 0);
+        k_scatter_partials<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, t_n.data(), p_stage, nslice, p_flags, G, rk);
+      } else if (ATs.wide())
+        k_transpose_partial_scatter<WARP_WIDE_RPL><<<grid_k3p_wide, WARP_THREADS, 0, stream>>>(
+          d_ctl.data(), ATs.warp_view_wide(), ybuf[0].data(), ybuf[1].data(), p_stage, nslice, p_flags, G, rk);
+      else
+        k_transpose_partial_scatter<1><<<grid_k3, WARP_THREADS, 0, stream>>>(
+          d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(), p_stage, nslice, p_flags, G, rk);
       k_interaction_slice<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, stage.data(), G, (size_t)nslice, x0, x1,
-                                                                 a0, a1, part_k3.data(), part_dy2.data(), grid_k2,
+                                                                 a0, a1, part_k3.data(), part_dy2.data(), n_part_dy2,
                                                                  d_flags.data() + DIST_FLAG_PARTIAL, p_scal, p_flags, G, rk);
       k_step_rule_gather<<<1, 32, 0, stream>>>(d_ctl.data(), scal.data(), G, d_flags.data() + DIST_FLAG_SCALARS);
       return;
@@ -608,14 +786,12 @@ struct pdlp_solver_t::impl_t {
                                                          ls.data() + j0, us.data() + j0, sum_x.data() + j0,
                                                          xbar.data() + j0);
     dist->allgather(xbar.data(), nslice, stream);
-    k_dual_step<<<grid_k2, WARP_THREADS, 0, stream>>>(d_ctl.data(), As.warp_view(), xbar.data(), ybuf[0].data(), ybuf[1].data(),
-                                                      lcs.data(), ucs.data(), sum_y.data(), part_dy2.data(), nullptr, 0);
-    k_transpose_partial<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
-                                                              dist_buf.data());
+    enqueue_k2(nullptr, 0);
+    launch_transpose_partial();
     dist->reduce_scatter(dist_buf.data(), rs_buf.data(), nslice, stream);
     peer_flags_t no_flags{};
     k_interaction_slice<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, rs_buf.data(), 1, 0, x0, x1, a0, a1,
-                                                               part_k3.data(), part_dy2.data(), grid_k2, nullptr, p_scal,
+                                                               part_k3.data(), part_dy2.data(), n_part_dy2, nullptr, p_scal,
                                                                no_flags, 1, rk);
     dist->allreduce(scal.data(), 3, false, stream);
     k_step_rule_gather<<<1, 32, 0, stream>>>(d_ctl.data(), scal.data(), 1, nullptr);
@@ -630,18 +806,14 @@ struct pdlp_solver_t::impl_t {
     k_primal_step<<<grid_k1, EW_THREADS, 0, stream>>>(d_ctl.data(), n, xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
                                                       atybuf[1].data(), cs.data(), ls.data(), us.data(), sum_x.data(),
                                                       xbar.data());
-    k_dual_step<<<grid_k2, WARP_THREADS, 0, stream>>>(d_ctl.data(), As.warp_view(), xbar.data(), ybuf[0].data(), ybuf[1].data(),
-                                                      lcs.data(), ucs.data(), sum_y.data(), part_dy2.data(), nullptr, 0);
+    enqueue_k2(nullptr, 0);
     if (!sharded()) {
-      k_transpose_step<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
-                                                             xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
-                                                             atybuf[1].data(), part_k3.data(), part_dy2.data(), grid_k2);
+      enqueue_k3();
       return;
     }
     // row-sharded: partial A_g^T y'_g and this rank's ||dy||^2 -> one all-reduce of n + 1 doubles -> K3b
-    k_transpose_partial<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
-                                                              dist_buf.data());
-    k_sum_partials<<<1, EW_THREADS, 0, stream>>>(d_ctl.data(), part_dy2.data(), grid_k2, 1, dist_buf.data() + n);
+    launch_transpose_partial();
+    k_sum_partials<<<1, EW_THREADS, 0, stream>>>(d_ctl.data(), part_dy2.data(), n_part_dy2, 1, dist_buf.data() + n);
     dist->allreduce(dist_buf.data(), (size_t)n + 1, false, stream);
     k_interaction_step<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, dist_buf.data(), xbuf[0].data(), xbuf[1].data(),
                                                           atybuf[0].data(), atybuf[1].data(), part_k3.data());
@@ -650,7 +822,7 @@ struct pdlp_solver_t::impl_t {
   void launch_attempts(int count)
   {
     if (count <= 0) return;
-    launches += (sharded() ? 5LL : 3LL) * count;  // kernels; collectives are not counted
+    launches += (long long)kernels_per_attempt() * count;  // kernels; collectives are not counted
     if (!use_graphs || count == 1) {
       for (int i = 0; i < count; ++i) enqueue_attempt();
       check_launch();
@@ -683,7 +855,7 @@ struct pdlp_solver_t::impl_t {
     CUOPT_CUDA_TRY(cudaEventRecord(ev_a, stream));
     if (need_aty) {  // pdhg.cu:183-202
       const int cur = h_ctl->parity;
-      k_spmv<<<grid_sp, WARP_THREADS, 0, stream>>>(ATs.warp_view(), ybuf[cur].data(), atybuf[cur].data());
+      launch_spmv(ATs, ybuf[cur].data(), atybuf[cur].data());
       if (sharded()) dist->allreduce(atybuf[cur].data(), n, false, stream);
       ++launches;
       need_aty = false;
@@ -760,8 +932,8 @@ struct pdlp_solver_t::impl_t {
       // row-sharded: the six row sums and both A^T y products are partial; combine over ranks, then the column pass
       k_sum_partials<<<1, EW_THREADS, 0, stream>>>(nullptr, part_rows.data(), grid_er, 6, d_scalar.data());
       dist->allreduce(d_scalar.data(), 6, false, stream);
-      k_spmv<<<grid_sp, WARP_THREADS, 0, stream>>>(AT.warp_view(), ybuf[cur].data(), dist_buf.data());
-      k_spmv<<<grid_sp, WARP_THREADS, 0, stream>>>(AT.warp_view(), y_avg.data(), dist_buf.data() + n);
+      launch_spmv(AT, ybuf[cur].data(), dist_buf.data());
+      launch_spmv(AT, y_avg.data(), dist_buf.data() + n);
       dist->allreduce(dist_buf.data(), 2 * (size_t)n, false, stream);
       k_eval_cols_from_aty<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, dist_buf.data(), dist_buf.data() + n,
                                                               xbuf[cur].data(), x_avg.data(), c.data(), l.data(), u.data(),
@@ -1096,14 +1268,9 @@ kernel_profile_t pdlp_solver_t::profile_kernels(int warmup_steps, int reps)
                                                           s.atybuf[0].data(), s.atybuf[1].data(), s.cs.data(), s.ls.data(),
                                                           s.us.data(), s.sum_x.data(), s.xbar.data());
     cudaEventRecord(ev[1], s.stream);
-    k_dual_step<<<s.grid_k2, WARP_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.As.warp_view(), s.xbar.data(), s.ybuf[0].data(),
-                                                          s.ybuf[1].data(), s.lcs.data(), s.ucs.data(), s.sum_y.data(),
-                                                          s.part_dy2.data(), nullptr, 0);
+    s.enqueue_k2(nullptr, 0);  // fused kernel, or block passes + epilogue
     cudaEventRecord(ev[2], s.stream);
-    k_transpose_step<<<s.grid_k3, WARP_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.ATs.warp_view(), s.ybuf[0].data(),
-                                                               s.ybuf[1].data(), s.xbuf[0].data(), s.xbuf[1].data(),
-                                                               s.atybuf[0].data(), s.atybuf[1].data(), s.part_k3.data(),
-                                                               s.part_dy2.data(), s.grid_k2);
+    s.enqueue_k3();
     cudaEventRecord(ev[3], s.stream);
     cudaEventSynchronize(ev[3]);
     if (r >= 3) {
@@ -1126,6 +1293,28 @@ kernel_profile_t pdlp_solver_t::profile_kernels(int warmup_steps, int reps)
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev[0], ev[1]);
   out.ms_iteration = ms / reps;
+  // the sharded solve's payload-free partial product on this A^T (scratch output), both block schedules
+  {
+    dvec<double> scratch((size_t)s.n);
+    for (int wide = 0; wide < 2; ++wide) {
+      if (wide && !s.ATs.wide()) break;
+      const int g = wide ? s.grid_k3p_wide : s.grid_k3;
+      for (int r = 0; r < reps + 3; ++r) {
+        if (r == 3) cudaEventRecord(ev[0], s.stream);
+        if (wide)
+          k_transpose_partial<WARP_WIDE_RPL><<<g, WARP_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.ATs.warp_view_wide(),
+                                                                              s.ybuf[0].data(), s.ybuf[1].data(), scratch.data());
+        else
+          k_transpose_partial<1><<<g, WARP_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.ATs.warp_view(), s.ybuf[0].data(),
+                                                                   s.ybuf[1].data(), scratch.data());
+      }
+      cudaEventRecord(ev[1], s.stream);
+      cudaEventSynchronize(ev[1]);
+      cudaEventElapsedTime(&ms, ev[0], ev[1]);
+      (wide ? out.ms_transpose_partial_wide : out.ms_transpose_partial) = ms / reps;
+    }
+    s.check_launch();
+  }
   for (auto& e : ev) cudaEventDestroy(e);
   s.sync();
   return out;

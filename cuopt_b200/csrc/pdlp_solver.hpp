@@ -18,6 +18,7 @@ struct kernel_profile_t {
   double ms_iteration = 0;  // average per attempt inside a batched run (all three kernels, back to back)
   int reps = 0;
   int grid_dual = 0, grid_transpose = 0, grid_primal = 0;
+  double ms_transpose_partial = 0, ms_transpose_partial_wide = 0;  // k_transpose_partial<1> / <WARP_WIDE_RPL>
 };
 
 // Optional multi-GPU context: rows of A are sharded over `world` ranks (see pdlp_dist.cu).

@@ -56,6 +56,9 @@ typedef struct cuOptB200KernelProfile {
   cuopt_float_t ms_iteration; /* mean per attempt, all three kernels back to back */
   cuopt_int_t reps;
   cuopt_int_t grid_primal, grid_dual, grid_transpose;
+  /* the payload-free partial transpose product of the sharded solve (k_transpose_partial) on this problem's A^T:
+   * blocks of <= 32 rows, and the wide schedule (<= 256 rows; 0 when A^T has >= 4 nonzeros per row on average) */
+  cuopt_float_t ms_transpose_partial, ms_transpose_partial_wide;
 } cuOptB200KernelProfile;
 
 /* Upload the problem to the current CUDA device (A, A^T, row-block schedules). */

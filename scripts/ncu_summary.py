@@ -41,10 +41,12 @@ def main():
                 i = hdr.index(key)
                 print(f"| {label} (`{key}`) | {r[i]} {units[i]} |")
         if "dram__bytes_read.sum" in hdr:
-            rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", ""))
-            wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", ""))
-            u = units[hdr.index("dram__bytes_read.sum")]
-            print(f"| **traffic = DRAM read + write** | {rd + wr:.3f} {u} |")
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}  # ncu scales each cell itself
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(key)
+                tot += float(r[i].replace(",", "")) * mult.get(units[i], 1.0)
+            print(f"| **traffic = DRAM read + write** | {tot / 1e6:.3f} Mbyte |")
         print()
 
 

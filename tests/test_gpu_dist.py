@@ -15,12 +15,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q, size, extra_cols, tol, mode, transport):
+def _worker(rank, world, port, q, size, extra_cols, tol, mode, transport, block_bytes):
     import torch
     import torch.distributed as dist
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       CUOPT_B200_DIST_MODE=transport)
+    if block_bytes:
+        os.environ["CUOPT_B200_GATHER_BLOCK_BYTES"] = str(block_bytes)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -41,12 +43,12 @@ def _worker(rank, world, port, q, size, extra_cols, tol, mode, transport):
         dist.destroy_process_group()
 
 
-def _solve_on_gpus(world, size, tol, mode, transport, extra_cols=0):
+def _solve_on_gpus(world, size, tol, mode, transport, extra_cols=0, block_bytes=0):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, size, extra_cols, tol, mode, transport))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, size, extra_cols, tol, mode, transport, block_bytes))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -125,3 +127,20 @@ def test_peer_store_transport_is_deterministic_and_equals_nccl_transport():
         assert other[0]["obj"] == a[0]["obj"] and other[0]["dobj"] == a[0]["dobj"]
         assert np.array_equal(other[0]["x"], a[0]["x"])
         assert all(np.array_equal(other[r]["y"], a[r]["y"]) for r in range(world))
+
+
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_two_gpu_solve_with_gather_blocking(transport):
+    """The large-LP kernels (column-blocked passes + element-wise epilogues / scatter) inside the sharded attempt:
+    forced on a small LP (4 blocks for A_g, 2 for A_g^T), they must reach the same optimum as the fused kernels."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    size, tol, world = 40_000, 1e-4, 2
+    fused = _solve_on_gpus(world, size, tol, 1, transport)
+    blocked = _solve_on_gpus(world, size, tol, 1, transport, block_bytes=100_000)
+    assert fused[0]["status"] == blocked[0]["status"] == 1
+    assert abs(blocked[0]["its"] - fused[0]["its"]) <= max(40, 0.4 * fused[0]["its"])
+    assert blocked[0]["obj"] == pytest.approx(fused[0]["obj"], rel=1e-3)  # both are tolerance-1e-4 points
+    lp, one = _single_gpu(size, tol, 1)
+    assert blocked[0]["obj"] == pytest.approx(lp.optimal_objective, rel=1e-3)
