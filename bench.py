@@ -78,6 +78,18 @@ class ClockSampler:
 
 
 WORKLOADS = {"c4": (10_000_000, 10_000_000), "c2": (1_000_000, 1_000_000)}
+# dram__bytes_read.sum + dram__bytes_write.sum per step of the dominant kernel (group), from the ncu captures under
+# profiles/ : (workload, kernel, blocked) -> (bytes, file)
+NCU_TRAFFIC = {
+    ("c4", "k_transpose_step", True): (649.8e6 + 735.8e6 + 381.0e6, "profiles/r1/ncu_full_c4_10M_blocked.md"),
+    ("c4", "k_dual_step", True): (650.6e6 + 741.0e6 + 496.3e6, "profiles/r1/ncu_full_c4_10M_blocked.md"),
+    ("c4", "k_transpose_step", False): (4028.1e6, "profiles/r1/ncu_full_c4_10M_hints_off.md"),
+    ("c4", "k_dual_step", False): (3804.4e6, "profiles/r1/ncu_full_c4_10M_hints_off.md"),
+    ("c3", "k_transpose_step", False): (20.13e6, "profiles/r1/ncu_full_c3_pds_shaped.md"),
+    ("c3", "k_dual_step", False): (17.93e6, "profiles/r1/ncu_full_c3_pds_shaped.md"),
+    ("c2", "k_transpose_step", False): (140.4e6, "profiles/r1/ncu_full_v4_warp_sync.md"),
+    ("c2", "k_dual_step", False): (145.0e6, "profiles/r1/ncu_full_v4_warp_sync.md"),
+}
 TRANSPORTS = {"p2p": "NVLink peer stores issued by the producing kernels (xbar slices, A_g^T y partials, 3 scalars); "
                      "no NCCL inside the PDHG loop",
               "nccl": "NCCL all-gather(xbar) + reduce-scatter(A_g^T y) + all-reduce(3 scalars) per attempt",
@@ -262,9 +274,15 @@ def main():
         dom = max(ks, key=lambda k: ks[k][0])
         ms, by = ks[dom]
         achieved = by / (ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
-                "algorithmic_bytes_per_launch": by, "ms_per_launch": ms}
+        blocks = {"k_dual_step": prof.blocks_dual, "k_transpose_step": prof.blocks_transpose}.get(dom, 1)
+        launched_as = dom if blocks <= 1 else (
+            f"{blocks} x k_block_pass + " + ("k_dual_epilogue" if dom == "k_dual_step" else "k_transpose_epilogue")
+            + " (gather blocking: the step's fused kernel split by column blocks, timed as one group)")
+        # DRAM traffic of that step from the committed `ncu --set full` capture of the same workload (bytes per step)
+        traffic, traffic_src = NCU_TRAFFIC.get((args.workload, dom, blocks > 1), (None, None))
+        roof = {"bound": "hbm", "kernel": dom, "launched_as": launched_as, "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_kind, "algorithmic_bytes_per_launch": by, "ms_per_launch": ms}
         b_iter = lp.algorithmic_bytes_per_iteration()
         extra = {"kernels": {k: {"ms": v[0], "algorithmic_GBps": v[1] / (v[0] * 1e-3) / 1e9} for k, v in ks.items()},
                  "iteration": {"ms_in_batch": prof.ms_iteration, "algorithmic_bytes": b_iter,

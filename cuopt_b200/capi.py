@@ -47,7 +47,8 @@ class KernelProfile(C.Structure):
                 ("bytes_primal_step", C.c_double), ("bytes_dual_step", C.c_double),
                 ("bytes_transpose_step", C.c_double), ("ms_iteration", C.c_double), ("reps", C.c_int32),
                 ("grid_primal", C.c_int32), ("grid_dual", C.c_int32), ("grid_transpose", C.c_int32),
-                ("ms_transpose_partial", C.c_double), ("ms_transpose_partial_wide", C.c_double)]
+                ("ms_transpose_partial", C.c_double), ("ms_transpose_partial_wide", C.c_double),
+                ("blocks_dual", C.c_int32), ("blocks_transpose", C.c_int32)]
 
 
 # every symbol include/*.h declares (tests check that the library exports all of them)

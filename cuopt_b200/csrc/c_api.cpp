@@ -706,6 +706,8 @@ cuopt_int_t cuOptB200SolverProfileKernels(cuOptB200Solver solver,
     profile->grid_transpose       = k.grid_transpose;
     profile->ms_transpose_partial      = k.ms_transpose_partial;
     profile->ms_transpose_partial_wide = k.ms_transpose_partial_wide;
+    profile->blocks_dual               = k.blocks_dual;
+    profile->blocks_transpose          = k.blocks_transpose;
   });
   return CUOPT_SUCCESS;
 }

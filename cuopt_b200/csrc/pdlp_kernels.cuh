@@ -906,7 +906,39 @@ __global__ void __launch_bounds__(SPMV_THREADS) k_eval_cols(pdhg_ctl_t* __restri
   eval_finalize(ctl, parts, parts_rows, n_parts_rows, k, out, red);
 }
 
-// Row-sharded mode: A^T y (current, average) arrives all-reduced in aty_cur / aty_avg; same column math, element-wise.
+// Row math of T1 on precomputed products ax_cur = A x_cur, ax_avg = A x_avg (element-wise; same parts layout as k_eval_rows).
+__global__ void __launch_bounds__(EW_THREADS) k_eval_rows_from_ax(int m,
+                                                                  const double* __restrict__ ax_cur,
+                                                                  const double* __restrict__ ax_avg,
+                                                                  const double* __restrict__ y_cur,
+                                                                  const double* __restrict__ y_avg,
+                                                                  const double* __restrict__ lc,
+                                                                  const double* __restrict__ uc,
+                                                                  double* __restrict__ parts)
+{
+  __shared__ double red[32];
+  double acc[6]    = {0, 0, 0, 0, 0, 0};
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const double lo = lc[i], hi = uc[i];
+    const double s[2]  = {__ldcs(ax_cur + i), __ldcs(ax_avg + i)};
+    const double yv[2] = {y_cur[i], y_avg[i]};
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const double viol = s[v] < lo ? lo - s[v] : (s[v] > hi ? s[v] - hi : 0.0);  // utils.cuh:166-178
+      acc[v] += viol * viol;
+      acc[2 + v] += bound_value_product(yv[v], lo, hi);
+      acc[4 + v] += yv[v] * yv[v];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const double t = block_reduce(acc[q], red);
+    if (threadIdx.x == 0) parts[q * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// A^T y (current, average) precomputed (all-reduced in the row-sharded mode): same column math as T2, element-wise.
 __global__ void __launch_bounds__(EW_THREADS) k_eval_cols_from_aty(pdhg_ctl_t* __restrict__ ctl,
                                                                    int n,
                                                                    const double* __restrict__ aty_cur,

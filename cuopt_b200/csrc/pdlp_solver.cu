@@ -23,7 +23,9 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <atomic>
 #include <map>
+#include <thread>
 #include <string>
 
 namespace cuopt_b200 {
@@ -61,12 +63,42 @@ struct csr_dev_t {
   }
 };
 
+// The greedy cuts below are sequential in nature; at 10M rows and a dozen schedules per solve they were ~0.5 s of
+// host time.  Rows are therefore cut in independent segments of SCHEDULE_SEGMENT rows (a block never spans a segment
+// boundary) that worker threads process in parallel; the segment results are concatenated in order, so the schedule
+// is the same run to run and independent of the thread count.
+constexpr int SCHEDULE_SEGMENT = 1 << 16;
+template <typename T, typename F>
+std::vector<T> cut_in_segments(int rows, F cut_segment)
+{
+  const int n_seg = std::max(1, (rows + SCHEDULE_SEGMENT - 1) / SCHEDULE_SEGMENT);
+  std::vector<std::vector<T>> part(n_seg);
+  const int n_thr = (int)std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)n_seg}));
+  std::atomic<int> next{0};
+  auto work = [&]() {
+    for (int sgm = next.fetch_add(1); sgm < n_seg; sgm = next.fetch_add(1))
+      cut_segment(sgm * SCHEDULE_SEGMENT, std::min(rows, (sgm + 1) * SCHEDULE_SEGMENT), part[sgm]);
+  };
+  if (n_thr <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_thr; ++t) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+  }
+  size_t total = 0;
+  for (auto& v : part) total += v.size();
+  std::vector<T> all;
+  all.reserve(total + 1);
+  for (auto& v : part) all.insert(all.end(), v.begin(), v.end());
+  return all;
+}
+
 // Cut consecutive rows into blocks of <= SPMV_NNZ nonzeros and <= SPMV_ROWS rows; a longer row is a block of its own.
 std::vector<int4> build_row_blocks(const std::vector<int>& off)
 {
-  std::vector<int4> blocks;
-  const int rows = (int)off.size() - 1;
-  int r          = 0;
+  const int all_rows = (int)off.size() - 1;
+  return cut_in_segments<int4>(all_rows, [&](int r, int rows, std::vector<int4>& blocks) {
   while (r < rows) {
     const int lo = off[r];
     int r1       = r;
@@ -78,7 +110,7 @@ std::vector<int4> build_row_blocks(const std::vector<int>& off)
     blocks.push_back(make_int4(r, r1, lo, off[r1]));
     r = r1;
   }
-  return blocks;
+  });
 }
 
 // Warp row blocks for the hot kernels: consecutive rows with <= WARP_NNZ nonzeros and <= max_rows rows (32, or
@@ -86,9 +118,8 @@ std::vector<int4> build_row_blocks(const std::vector<int>& off)
 // {first row, first nnz}.
 std::vector<int2> build_warp_blocks(const std::vector<int>& off, int max_rows = 32)
 {
-  std::vector<int2> wd;
-  const int rows = (int)off.size() - 1;
-  int r          = 0;
+  const int all_rows = (int)off.size() - 1;
+  std::vector<int2> wd = cut_in_segments<int2>(all_rows, [&](int r, int rows, std::vector<int2>& wd) {
   while (r < rows) {
     const int lo = off[r];
     int r1       = r;
@@ -100,7 +131,8 @@ std::vector<int2> build_warp_blocks(const std::vector<int>& off, int max_rows = 
     wd.push_back(make_int2(r, lo));
     r = r1;
   }
-  wd.push_back(make_int2(rows, off[rows]));
+  });
+  wd.push_back(make_int2(all_rows, off[all_rows]));
   return wd;
 }
 
@@ -220,7 +252,9 @@ struct pdlp_solver_t::impl_t {
   pdhg_ctl_t* h_ctl = nullptr;  // pinned mirrors
   eval_t* h_eval    = nullptr;
   double* h_scalar  = nullptr;
-  int grid_sp = 1, grid_sp_wide = 1, grid_k3p_wide = 1;
+  int grid_sp = 1, grid_sp_wide = 1, grid_k3p_wide = 1, occ_spmv = 1, occ_spmv_wide = 1;
+  bool eval_tma = false;
+  dvec<double> eval_m, eval_n;  // A x (current, average) and, on one GPU, A^T y (current, average)
   // gather blocking (pdlp_kernels.cuh): the scaled A / A^T cut into column blocks whose slice of the gathered vector
   // is L2-sized; B == 1 (small LPs) keeps the fused kernels
   struct gather_blocks_t {
@@ -231,7 +265,7 @@ struct pdlp_solver_t::impl_t {
   };
   gather_blocks_t blkA, blkAT;
   dvec<double> t_m, t_n;
-  size_t gather_block_bytes = 32u << 20;
+  size_t gather_block_bytes = 40u << 20;  // measured optimum at configs[3] (profiles/r1/gather_block_sweep_c4.txt)
   int n_part_dy2 = 1;  // CTAs that publish ||dy||^2 partials: grid_k2 (fused K2) or grid_m (blocked K2 epilogue)
   int grid_k1 = 1, grid_k2 = 1, grid_k3 = 1, grid_er = 1, grid_ec = 1, grid_n = 1, grid_m = 1, grid_misc = 1;
   std::map<int, cudaGraphExec_t> graphs;
@@ -386,7 +420,17 @@ struct pdlp_solver_t::impl_t {
     // size of the slice of the gathered vector one column block may span (0 = never block); bytes, for the tests too
     if (const char* e = std::getenv("CUOPT_B200_GATHER_BLOCK_BYTES")) gather_block_bytes = (size_t)std::atoll(e);
     part_k3.resize(2 * (size_t)std::max(grid_k3, grid_n));
-    part_rows.resize(6 * (size_t)grid_er);
+    part_rows.resize(6 * (size_t)std::max(grid_er, grid_m));
+    // evaluation of the iterates: four SpMVs on the warp-block core + element-wise row / column math (default), or the
+    // two CTA-level TMA-pipeline kernels that handle two vectors per pass (CUOPT_B200_EVAL=tma; measured 3x slower at
+    // configs[3], profiles/r1/launch_list_c4_bench.md)
+    if (const char* e = std::getenv("CUOPT_B200_EVAL")) eval_tma = std::string(e) == "tma";
+    if (!eval_tma) {
+      eval_m.resize(2 * (size_t)m);
+      if (!sharded()) eval_n.resize(2 * (size_t)n);
+    }
+    CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_spmv, (const void*)k_spmv<1>, WARP_THREADS, 0));
+    CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_spmv_wide, (const void*)k_spmv<WARP_WIDE_RPL>, WARP_THREADS, 0));
     part_cols.resize(8 * (size_t)std::max(grid_ec, grid_n));
     part_misc.resize(2 * (size_t)std::max(grid_misc, ew_grid(nnz, sms)));
     d_scalar.resize(8);
@@ -753,8 +797,13 @@ struct pdlp_solver_t::impl_t {
   // out = M v on the warp-block scheme
   void launch_spmv(const csr_dev_t& M, const double* v, double* out)
   {
-    if (M.wide()) k_spmv<WARP_WIDE_RPL><<<grid_sp_wide, WARP_THREADS, 0, stream>>>(M.warp_view_wide(), v, out);
-    else k_spmv<1><<<grid_sp, WARP_THREADS, 0, stream>>>(M.warp_view(), v, out);
+    auto grid = [&](int n_wb, int occ) {
+      return std::max(1, std::min((n_wb + WARP_PER_CTA - 1) / WARP_PER_CTA, sms * std::max(occ, 1)));
+    };
+    if (M.wide())
+      k_spmv<WARP_WIDE_RPL><<<grid(M.n_wb_wide, occ_spmv_wide), WARP_THREADS, 0, stream>>>(M.warp_view_wide(), v, out);
+    else
+      k_spmv<1><<<grid(M.n_wb, occ_spmv), WARP_THREADS, 0, stream>>>(M.warp_view(), v, out);
   }
 
   // scheme (ii): this rank updates only its slice of the primal side (kernel comments in pdlp_kernels.cuh)
@@ -921,24 +970,42 @@ struct pdlp_solver_t::impl_t {
                                                              x_avg.data(), Dc.data());
     k_average_and_unscale<<<grid_m, EW_THREADS, 0, stream>>>(d_ctl.data(), mode, m, ybuf[cur].data(), sum_y.data(),
                                                              y_avg.data(), Dr.data());
-    k_eval_rows<<<grid_er, SPMV_THREADS, SMEM_EVAL, stream>>>(A.view(), xbuf[cur].data(), x_avg.data(), ybuf[cur].data(),
-                                                      y_avg.data(), lc.data(), uc.data(), part_rows.data());
-    if (!sharded()) {
+    int n_rows_parts = grid_er;
+    if (eval_tma) {
+      k_eval_rows<<<grid_er, SPMV_THREADS, SMEM_EVAL, stream>>>(A.view(), xbuf[cur].data(), x_avg.data(), ybuf[cur].data(),
+                                                                y_avg.data(), lc.data(), uc.data(), part_rows.data());
+    } else {
+      launch_spmv(A, xbuf[cur].data(), eval_m.data());
+      launch_spmv(A, x_avg.data(), eval_m.data() + m);
+      k_eval_rows_from_ax<<<grid_m, EW_THREADS, 0, stream>>>(m, eval_m.data(), eval_m.data() + m, ybuf[cur].data(),
+                                                             y_avg.data(), lc.data(), uc.data(), part_rows.data());
+      n_rows_parts = grid_m;
+      launches += 2;
+    }
+    if (!sharded() && eval_tma) {
       k_eval_cols<<<grid_ec, SPMV_THREADS, SMEM_EVAL, stream>>>(d_ctl.data(), AT.view(), xbuf[cur].data(), x_avg.data(),
                                                         ybuf[cur].data(), y_avg.data(), c.data(), l.data(), u.data(),
                                                         rc_cur.data(), rc_avg.data(), part_cols.data(), part_rows.data(),
                                                         grid_er, eval_consts(), d_eval.data());
     } else {
-      // row-sharded: the six row sums and both A^T y products are partial; combine over ranks, then the column pass
-      k_sum_partials<<<1, EW_THREADS, 0, stream>>>(nullptr, part_rows.data(), grid_er, 6, d_scalar.data());
-      dist->allreduce(d_scalar.data(), 6, false, stream);
-      launch_spmv(AT, ybuf[cur].data(), dist_buf.data());
-      launch_spmv(AT, y_avg.data(), dist_buf.data() + n);
-      dist->allreduce(dist_buf.data(), 2 * (size_t)n, false, stream);
-      k_eval_cols_from_aty<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, dist_buf.data(), dist_buf.data() + n,
-                                                              xbuf[cur].data(), x_avg.data(), c.data(), l.data(), u.data(),
-                                                              rc_cur.data(), rc_avg.data(), part_cols.data(),
-                                                              d_scalar.data(), 1, eval_consts(), d_eval.data());
+      // A^T y for both iterates, then the column math element-wise.  Row-sharded: the six row sums and both products
+      // are partial and are combined over the ranks first.
+      double* aty2            = sharded() ? dist_buf.data() : eval_n.data();
+      const double* rows_src  = part_rows.data();
+      int rows_count          = n_rows_parts;
+      if (sharded()) {
+        k_sum_partials<<<1, EW_THREADS, 0, stream>>>(nullptr, part_rows.data(), n_rows_parts, 6, d_scalar.data());
+        dist->allreduce(d_scalar.data(), 6, false, stream);
+        rows_src   = d_scalar.data();
+        rows_count = 1;
+      }
+      launch_spmv(AT, ybuf[cur].data(), aty2);
+      launch_spmv(AT, y_avg.data(), aty2 + n);
+      if (sharded()) dist->allreduce(aty2, 2 * (size_t)n, false, stream);
+      k_eval_cols_from_aty<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, aty2, aty2 + n, xbuf[cur].data(), x_avg.data(),
+                                                              c.data(), l.data(), u.data(), rc_cur.data(), rc_avg.data(),
+                                                              part_cols.data(), rows_src, rows_count, eval_consts(),
+                                                              d_eval.data());
       launches += 3;
     }
     launches += 4;
@@ -1251,6 +1318,7 @@ kernel_profile_t pdlp_solver_t::profile_kernels(int warmup_steps, int reps)
   kernel_profile_t out;
   out.reps = reps;
   out.grid_primal = s.grid_k1; out.grid_dual = s.grid_k2; out.grid_transpose = s.grid_k3;
+  out.blocks_dual = s.blkA.B; out.blocks_transpose = s.blkAT.B;
   // SURVEY.md §8(d) per-kernel algorithmic bytes (gathers counted once per vector element)
   const double n = s.n, m = s.m, nz = s.nnz;
   out.bytes_primal_step    = 8.0 * (5 * n + 2 * n + 2 * n);                       // x,c,AtY,l,u | x',xbar | sum_x r/w

@@ -19,6 +19,7 @@ struct kernel_profile_t {
   int reps = 0;
   int grid_dual = 0, grid_transpose = 0, grid_primal = 0;
   double ms_transpose_partial = 0, ms_transpose_partial_wide = 0;  // k_transpose_partial<1> / <WARP_WIDE_RPL>
+  int blocks_dual = 1, blocks_transpose = 1;                       // gather blocking (1 = fused kernel)
 };
 
 // Optional multi-GPU context: rows of A are sharded over `world` ranks (see pdlp_dist.cu).

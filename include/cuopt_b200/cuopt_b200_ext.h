@@ -59,6 +59,9 @@ typedef struct cuOptB200KernelProfile {
   /* the payload-free partial transpose product of the sharded solve (k_transpose_partial) on this problem's A^T:
    * blocks of <= 32 rows, and the wide schedule (<= 256 rows; 0 when A^T has >= 4 nonzeros per row on average) */
   cuopt_float_t ms_transpose_partial, ms_transpose_partial_wide;
+  /* gather blocking: > 1 means the "dual" / "transpose" step is that many k_block_pass launches + one element-wise
+   * epilogue instead of the single fused kernel (their times above are those of the whole group) */
+  cuopt_int_t blocks_dual, blocks_transpose;
 } cuOptB200KernelProfile;
 
 /* Upload the problem to the current CUDA device (A, A^T, row-block schedules). */
