@@ -58,6 +58,7 @@ struct eval_t {
   double l2_primal_variable, l2_dual_variable;
   int status;  // termination_status_t; 6 (NumericalError) == "keep going" as in termination_strategy.cu:186
   int pad;
+  double linf_relative_primal_residual, linf_relative_dual_residual;  // per_constraint_residual only, else 0
 };
 
 struct eval_consts_t {
@@ -65,6 +66,7 @@ struct eval_consts_t {
   double abs_gap_tol, rel_gap_tol, abs_primal_tol, rel_primal_tol, abs_dual_tol, rel_dual_tol;
   double l2_norm_b, l2_norm_c;
   int reduced_cost_rule;  // 1: handle_some_primal_gradients_on_finite_bounds_as_residuals
+  int per_constraint_residual;  // feasibility tests on linf(residual_i - rel * rhs_i) <= abs (termination_strategy.cu:141-166)
 };
 
 // Publish per-CTA partial sums and elect the last CTA to finish (returns true in every thread of
@@ -791,12 +793,30 @@ __device__ __forceinline__ void eval_column(int j, const double (&s)[2], double 
 // Final scalars of the evaluation, run by the last CTA of the column pass (all its threads enter).
 // parts: 8 x gridDim.x column partials; parts_rows: 6 x n_parts_rows row partials
 // ({viol^2, y-part of the dual objective, ||y||^2} x {cur, avg}).
+// max of `count` published partials (all >= 0 or seeded with 0); result in all threads
+__device__ __forceinline__ double gather_partials_max(const double* parts, int count, double* red)
+{
+  double s = 0.0;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) s = fmax(s, __ldcg(parts + i));
+  return block_reduce<true>(s, red);
+}
+
+// max_cols: 2 x gridDim.x column maxima, max_rows: 2 x n_max_rows row maxima (per_constraint_residual), else nullptr
 __device__ __forceinline__ void eval_finalize(pdhg_ctl_t* ctl, const double* parts, const double* parts_rows,
-                                              int n_parts_rows, const eval_consts_t& k, eval_t* out, double* red)
+                                              int n_parts_rows, const eval_consts_t& k, eval_t* out, double* red,
+                                              const double* max_cols = nullptr, const double* max_rows = nullptr,
+                                              int n_max_rows = 0)
 {
   double tot[14];
   for (int q = 0; q < 8; ++q) tot[q] = gather_partials(parts + q * gridDim.x, gridDim.x, red);
   for (int q = 0; q < 6; ++q) tot[8 + q] = gather_partials(parts_rows + q * n_parts_rows, n_parts_rows, red);
+  double linf_p[2] = {0.0, 0.0}, linf_d[2] = {0.0, 0.0};
+  if (k.per_constraint_residual && max_cols != nullptr && max_rows != nullptr) {
+    for (int v = 0; v < 2; ++v) {
+      linf_d[v] = gather_partials_max(max_cols + v * gridDim.x, gridDim.x, red);
+      linf_p[v] = gather_partials_max(max_rows + v * n_max_rows, n_max_rows, red);
+    }
+  }
   if (threadIdx.x != 0) return;
   const double pw = ctl->primal_weight;
   for (int v = 0; v < 2; ++v) {
@@ -817,8 +837,14 @@ __device__ __forceinline__ void eval_finalize(pdhg_ctl_t* ctl, const double* par
     e.l2_dual_variable   = sqrt(tot[8 + 4 + v]);
     // termination_strategy.cu:117-250 (l2 criteria)
     const bool gap_ok    = e.gap <= k.abs_gap_tol + k.rel_gap_tol * e.abs_objective;
-    const bool primal_ok = e.l2_primal_residual <= k.abs_primal_tol + k.rel_primal_tol * k.l2_norm_b;
-    const bool dual_ok   = e.l2_dual_residual <= k.abs_dual_tol + k.rel_dual_tol * k.l2_norm_c;
+    bool primal_ok = e.l2_primal_residual <= k.abs_primal_tol + k.rel_primal_tol * k.l2_norm_b;
+    bool dual_ok   = e.l2_dual_residual <= k.abs_dual_tol + k.rel_dual_tol * k.l2_norm_c;
+    e.linf_relative_primal_residual = linf_p[v];
+    e.linf_relative_dual_residual   = linf_d[v];
+    if (k.per_constraint_residual) {  // termination_strategy.cu:141-166: absolute tolerance only
+      primal_ok = linf_p[v] <= k.abs_primal_tol;
+      dual_ok   = linf_d[v] <= k.abs_dual_tol;
+    }
     e.status             = (dual_ok && primal_ok && gap_ok) ? 1 : (primal_ok ? 7 : 6);
     // pdlp_restart_strategy.cu:367-380
     const double w2 = pw * pw;
@@ -914,27 +940,50 @@ __global__ void __launch_bounds__(EW_THREADS) k_eval_rows_from_ax(int m,
                                                                   const double* __restrict__ y_avg,
                                                                   const double* __restrict__ lc,
                                                                   const double* __restrict__ uc,
-                                                                  double* __restrict__ parts)
+                                                                  double* __restrict__ parts,
+                                                                  double rel_primal_tol,
+                                                                  double* __restrict__ parts_max)  // 2 x gridDim.x or null
 {
   __shared__ double red[32];
   double acc[6]    = {0, 0, 0, 0, 0, 0};
+  double mx[2]     = {0.0, 0.0};  // per_constraint_residual: max_i (violation_i - rel * b_i), seeded with 0
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
     const double lo = lc[i], hi = uc[i];
     const double s[2]  = {__ldcs(ax_cur + i), __ldcs(ax_avg + i)};
     const double yv[2] = {y_cur[i], y_avg[i]};
+    // combine_finite_abs_bounds (utils.cuh:140-148)
+    const double b = fmax(isfinite(lo) ? fabs(lo) : 0.0, isfinite(hi) ? fabs(hi) : 0.0);
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       const double viol = s[v] < lo ? lo - s[v] : (s[v] > hi ? s[v] - hi : 0.0);  // utils.cuh:166-178
       acc[v] += viol * viol;
       acc[2 + v] += bound_value_product(yv[v], lo, hi);
       acc[4 + v] += yv[v] * yv[v];
+      mx[v] = fmax(mx[v], viol - rel_primal_tol * b);
     }
   }
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
     const double t = block_reduce(acc[q], red);
     if (threadIdx.x == 0) parts[q * gridDim.x + blockIdx.x] = t;
+  }
+  if (parts_max != nullptr) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const double t = block_reduce<true>(mx[v], red);
+      if (threadIdx.x == 0) parts_max[v * gridDim.x + blockIdx.x] = t;
+    }
+  }
+}
+// out[v] = max over `count` per-CTA maxima (one CTA); the row-sharded evaluation all-reduces them with MAX
+__global__ void __launch_bounds__(EW_THREADS) k_max_partials(const double* __restrict__ parts, int count, int n_quantities,
+                                                             double* __restrict__ out)
+{
+  __shared__ double red[32];
+  for (int q = 0; q < n_quantities; ++q) {
+    const double t = gather_partials_max(parts + q * count, count, red);
+    if (threadIdx.x == 0) out[q] = t;
   }
 }
 
@@ -954,18 +1003,34 @@ __global__ void __launch_bounds__(EW_THREADS) k_eval_cols_from_aty(pdhg_ctl_t* _
                                                                    const double* __restrict__ parts_rows,
                                                                    int n_parts_rows,
                                                                    eval_consts_t k,
-                                                                   eval_t* __restrict__ out)
+                                                                   eval_t* __restrict__ out,
+                                                                   double* __restrict__ parts_max,  // 2 x gridDim.x or null
+                                                                   const double* __restrict__ max_rows,
+                                                                   int n_max_rows)
 {
   __shared__ double red[32];
   double acc[8]    = {0, 0, 0, 0, 0, 0, 0, 0};
+  double mx[2]     = {0.0, 0.0};  // per_constraint_residual: max_j ((g - rc)_j - rel * c_j), signed (utils.cuh:392-404)
   const int stride = gridDim.x * blockDim.x;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
     const double s[2]  = {aty_cur[j], aty_avg[j]};
     const double xv[2] = {x_cur[j], x_avg[j]};
-    eval_column(j, s, c[j], l[j], u[j], xv, k.reduced_cost_rule, rc_cur, rc_avg, acc);
+    const double cj    = c[j];
+    eval_column(j, s, cj, l[j], u[j], xv, k.reduced_cost_rule, rc_cur, rc_avg, acc);
+    if (parts_max != nullptr) {
+      mx[0] = fmax(mx[0], ((cj - s[0]) - rc_cur[j]) - k.rel_dual_tol * cj);
+      mx[1] = fmax(mx[1], ((cj - s[1]) - rc_avg[j]) - k.rel_dual_tol * cj);
+    }
+  }
+  if (parts_max != nullptr) {  // published ahead of the ticket of publish_and_elect (its fence covers these stores)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const double t = block_reduce<true>(mx[v], red);
+      if (threadIdx.x == 0) parts_max[v * gridDim.x + blockIdx.x] = t;
+    }
   }
   if (!publish_and_elect<8>(acc, parts, &ctl->ticket[1], red)) return;
-  eval_finalize(ctl, parts, parts_rows, n_parts_rows, k, out, red);
+  eval_finalize(ctl, parts, parts_rows, n_parts_rows, k, out, red, parts_max, max_rows, n_max_rows);
 }
 
 // Averages + in-place unscaling ahead of the evaluation (pdlp.cu:1103-1136,

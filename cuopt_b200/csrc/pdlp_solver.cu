@@ -255,6 +255,7 @@ struct pdlp_solver_t::impl_t {
   int grid_sp = 1, grid_sp_wide = 1, grid_k3p_wide = 1, occ_spmv = 1, occ_spmv_wide = 1;
   bool eval_tma = false;
   dvec<double> eval_m, eval_n;  // A x (current, average) and, on one GPU, A^T y (current, average)
+  dvec<double> part_max;        // per_constraint_residual: per-CTA maxima, rows (2 x grid_m) then columns (2 x grid_n)
   // gather blocking (pdlp_kernels.cuh): the scaled A / A^T cut into column blocks whose slice of the gathered vector
   // is L2-sized; B == 1 (small LPs) keeps the fused kernels
   struct gather_blocks_t {
@@ -425,6 +426,10 @@ struct pdlp_solver_t::impl_t {
     // two CTA-level TMA-pipeline kernels that handle two vectors per pass (CUOPT_B200_EVAL=tma; measured 3x slower at
     // configs[3], profiles/r1/launch_list_c4_bench.md)
     if (const char* e = std::getenv("CUOPT_B200_EVAL")) eval_tma = std::string(e) == "tma";
+    if (st.per_constraint_residual) {  // the linf residuals are only implemented on the element-wise evaluation path
+      eval_tma = false;
+      part_max.resize(2 * (size_t)std::max(grid_m, grid_n) * 2);
+    }
     if (!eval_tma) {
       eval_m.resize(2 * (size_t)m);
       if (!sharded()) eval_n.resize(2 * (size_t)n);
@@ -433,7 +438,7 @@ struct pdlp_solver_t::impl_t {
     CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_spmv_wide, (const void*)k_spmv<WARP_WIDE_RPL>, WARP_THREADS, 0));
     part_cols.resize(8 * (size_t)std::max(grid_ec, grid_n));
     part_misc.resize(2 * (size_t)std::max(grid_misc, ew_grid(nnz, sms)));
-    d_scalar.resize(8);
+    d_scalar.resize(12);
     if (sharded()) setup_transport();
     d_ticket.resize(4);
     d_ticket.zero(stream);
@@ -957,6 +962,7 @@ struct pdlp_solver_t::impl_t {
     k.l2_norm_b                = l2_norm_b;
     k.l2_norm_c                = l2_norm_c;
     k.reduced_cost_rule        = hp.handle_some_primal_gradients_on_finite_bounds_as_residuals ? 1 : 0;
+    k.per_constraint_residual  = st.per_constraint_residual ? 1 : 0;
     return k;
   }
 
@@ -978,7 +984,9 @@ struct pdlp_solver_t::impl_t {
       launch_spmv(A, xbuf[cur].data(), eval_m.data());
       launch_spmv(A, x_avg.data(), eval_m.data() + m);
       k_eval_rows_from_ax<<<grid_m, EW_THREADS, 0, stream>>>(m, eval_m.data(), eval_m.data() + m, ybuf[cur].data(),
-                                                             y_avg.data(), lc.data(), uc.data(), part_rows.data());
+                                                             y_avg.data(), lc.data(), uc.data(), part_rows.data(),
+                                                             st.relative_primal_tolerance,
+                                                             st.per_constraint_residual ? part_max.data() : nullptr);
       n_rows_parts = grid_m;
       launches += 2;
     }
@@ -1002,10 +1010,24 @@ struct pdlp_solver_t::impl_t {
       launch_spmv(AT, ybuf[cur].data(), aty2);
       launch_spmv(AT, y_avg.data(), aty2 + n);
       if (sharded()) dist->allreduce(aty2, 2 * (size_t)n, false, stream);
+      double* max_cols       = nullptr;
+      const double* max_rows = nullptr;
+      int max_rows_count     = 0;
+      if (st.per_constraint_residual) {
+        max_rows       = part_max.data();
+        max_rows_count = grid_m;
+        max_cols       = part_max.data() + 2 * (size_t)std::max(grid_m, grid_n);
+        if (sharded()) {  // the row maxima of the other ranks' blocks
+          k_max_partials<<<1, EW_THREADS, 0, stream>>>(part_max.data(), grid_m, 2, d_scalar.data() + 8);
+          dist->allreduce(d_scalar.data() + 8, 2, true, stream);
+          max_rows       = d_scalar.data() + 8;
+          max_rows_count = 1;
+        }
+      }
       k_eval_cols_from_aty<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, aty2, aty2 + n, xbuf[cur].data(), x_avg.data(),
                                                               c.data(), l.data(), u.data(), rc_cur.data(), rc_avg.data(),
                                                               part_cols.data(), rows_src, rows_count, eval_consts(),
-                                                              d_eval.data());
+                                                              d_eval.data(), max_cols, max_rows, max_rows_count);
       launches += 3;
     }
     launches += 4;

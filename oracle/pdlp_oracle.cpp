@@ -81,6 +81,7 @@ struct settings_t {
   int iteration_limit;
   double time_limit;
   int num_threads;
+  int per_constraint_residual;  // convergence_information.cu:163-204, termination_strategy.cu:141-166
 };
 
 struct stats_t {
@@ -189,6 +190,7 @@ inline double div_check_zero(double a, double b) { return b == 0.0 ? 0.0 : a / b
 
 struct convergence_t {  // termination_strategy/convergence_information.cu
   double l2_primal_residual = 0, l2_dual_residual = 0, primal_objective = 0, dual_objective = 0;
+  double linf_relative_primal_residual = 0, linf_relative_dual_residual = 0;  // per_constraint_residual only
   double gap = 0, abs_objective = 0, l2_primal_variable = 0, l2_dual_variable = 0;
   std::vector<double> reduced_cost;
   int status = 6;
@@ -234,6 +236,7 @@ class oracle_t {
   // {current primal, current dual, primal average, dual average, current A^T y, sum primal, sum dual,
   //  last-restart primal, last-restart dual} and 8 scalars {primal weight, step size, total pdlp iterations,
   //  total pdhg iterations, last candidate kkt, last restart kkt, sum of solution weights, iterations since restart}
+  double last_linf[2] = {0, 0};  // per-constraint residuals of the last pdlp_oracle_convergence call
   bool warm_given = false;
   std::vector<double> warm_v[9];
   double warm_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -550,8 +553,20 @@ class oracle_t {
     // termination_strategy.cu:117-250 (per_constraint_residual = false, no infeasibility detection)
     cv.status              = 6;  // "NumericalError" == keep going (:186)
     const bool optimal_gap = cv.gap <= st.abs_gap_tol + st.rel_gap_tol * cv.abs_objective;
-    const bool primal_feas = cv.l2_primal_residual <= st.abs_primal_tol + st.rel_primal_tol * l2_norm_b;
-    const bool dual_feas   = cv.l2_dual_residual <= st.abs_dual_tol + st.rel_dual_tol * l2_norm_c;
+    bool primal_feas       = cv.l2_primal_residual <= st.abs_primal_tol + st.rel_primal_tol * l2_norm_b;
+    bool dual_feas         = cv.l2_dual_residual <= st.abs_dual_tol + st.rel_dual_tol * l2_norm_c;
+    if (st.per_constraint_residual) {
+      // linf of (residual_i - rel * rhs_i), reduction seeded with 0 (convergence_information.cu:163-204,
+      // utils.cuh:392-404: the dual residual and c enter SIGNED); compared with the ABSOLUTE tolerance only
+      // (termination_strategy.cu:141-166)
+      double lp = 0.0, ld = 0.0;
+      for (int i = 0; i < m; ++i) lp = std::max(lp, violation(tmp_m[i], lc[i], uc[i]) - st.rel_primal_tol * b_comb[i]);
+      for (int j = 0; j < n; ++j) ld = std::max(ld, (tmp_n[j] - cv.reduced_cost[j]) - st.rel_dual_tol * c[j]);
+      cv.linf_relative_primal_residual = lp;
+      cv.linf_relative_dual_residual   = ld;
+      primal_feas                      = lp <= st.abs_primal_tol;
+      dual_feas                        = ld <= st.abs_dual_tol;
+    }
     if (dual_feas && primal_feas && optimal_gap) cv.status = 1;
     else if (primal_feas) cv.status = 7;
   }
@@ -810,6 +825,8 @@ void pdlp_oracle_convergence(void* h, const double* px, const double* py, double
   out8[0] = cv.l2_primal_residual; out8[1] = cv.l2_dual_residual; out8[2] = cv.primal_objective;
   out8[3] = cv.dual_objective; out8[4] = cv.gap; out8[5] = cv.abs_objective; out8[6] = cv.status;
   out8[7] = o->primal_weight > 0 ? o->kkt_score(cv) : 0.0;
+  o->last_linf[0] = cv.linf_relative_primal_residual;
+  o->last_linf[1] = cv.linf_relative_dual_residual;
   if (reduced_cost) std::memcpy(reduced_cost, cv.reduced_cost.data(), sizeof(double) * o->n);
 }
 
@@ -874,6 +891,8 @@ double pdlp_oracle_get_scalar(void* h, const char* name)
   if (s == "last_restart_kkt") return o->last_restart_kkt;
   if (s == "last_candidate_kkt") return o->last_candidate_kkt;
   if (s == "n_restarts") return o->n_restarts;
+  if (s == "linf_relative_primal_residual") return o->last_linf[0];
+  if (s == "linf_relative_dual_residual") return o->last_linf[1];
   return std::numeric_limits<double>::quiet_NaN();
 }
 // Major-iteration trace: 12 doubles per row (k, restarted, to_average, p, d, gap, rp, rd, step, weight, kkt_cur, kkt_avg)

@@ -54,6 +54,7 @@ class Settings(C.Structure):
         ("abs_primal_tol", C.c_double), ("rel_primal_tol", C.c_double),
         ("abs_gap_tol", C.c_double), ("rel_gap_tol", C.c_double),
         ("iteration_limit", C.c_int), ("time_limit", C.c_double), ("num_threads", C.c_int),
+        ("per_constraint_residual", C.c_int),
     ]
 
 
@@ -168,7 +169,7 @@ class Oracle:
 
     def __init__(self, offsets, indices, values, c, var_lb, var_ub, con_lb, con_ub, *, maximize=False,
                  objective_offset=0.0, mode=STABLE2, hyper: Hyper | None = None, tol=1e-4, iteration_limit=2**31 - 1,
-                 time_limit=float("inf"), tolerances: dict | None = None):
+                 time_limit=float("inf"), tolerances: dict | None = None, per_constraint_residual=False):
         L = lib()
         self.m, self.n = len(con_lb), len(c)
         self._keep = [np.ascontiguousarray(offsets, np.int32), np.ascontiguousarray(indices, np.int32)] + [
@@ -178,7 +179,8 @@ class Oracle:
                  rel_gap_tol=tol)
         if tolerances:
             t.update(tolerances)
-        self.settings = Settings(iteration_limit=int(iteration_limit), time_limit=float(time_limit), num_threads=0, **t)
+        self.settings = Settings(iteration_limit=int(iteration_limit), time_limit=float(time_limit), num_threads=0,
+                                 per_constraint_residual=int(bool(per_constraint_residual)), **t)
         k = self._keep
         self.h = C.c_void_p(L.pdlp_oracle_create(
             C.c_int(self.m), C.c_int(self.n), _p(k[0]), _p(k[1]), _p(k[2]), _p(k[3]), _p(k[4]), _p(k[5]), _p(k[6]),

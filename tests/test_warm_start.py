@@ -156,3 +156,64 @@ def test_solution_without_capture_has_no_warm_start():
     sol = gpu_solve(gpu_problem(lp_arrays(lpgen.sparse_lp(300, 250, 5, seed=3))), 1e-2, capture=False)
     with pytest.raises(capi.CuOptError):
         sol.warm_start()
+
+
+# ------------------------------------------------------------------- per_constraint_residual (reference pin)
+def per_constraint_case():
+    """The LP of the reference's per_constraint_test (cpp/tests/linear_programming/pdlp_test.cu:633-716): 3 x 3 identity,
+    b = 0, c = 0, iterate x = (0.02, 0.03, 0.1): ||r||_2 = 0.1063 > 0.1 but max_i r_i = 0.1 <= 0.1."""
+    a = dict(offsets=np.array([0, 1, 2, 3], np.int32), indices=np.array([0, 1, 2], np.int32), values=np.ones(3),
+             c=np.zeros(3), var_lb=np.zeros(3), var_ub=np.full(3, np.inf), con_lb=np.zeros(3), con_ub=np.zeros(3))
+    x = np.array([0.02, 0.03, 0.1])
+    z = np.zeros(3)
+    warm = dict(current_primal_solution=x, current_dual_solution=z, initial_primal_average=x, initial_dual_average=z,
+                current_ATY=z, sum_primal_solutions=z, sum_dual_solutions=z, last_restart_duality_gap_primal_solution=z,
+                last_restart_duality_gap_dual_solution=z, initial_primal_weight=1.0, initial_step_size=0.1,
+                total_pdlp_iterations=40, total_pdhg_iterations=40, last_candidate_kkt_score=1.0,
+                last_restart_kkt_score=1.0, sum_solution_weight=0.0, iterations_since_last_restart=0)
+    tol = dict(abs_primal_tol=0.1, rel_primal_tol=0.0, abs_dual_tol=0.1, rel_dual_tol=0.0)
+    return a, x, warm, tol
+
+
+def test_oracle_per_constraint_residual_matches_the_reference_test():
+    a, x, warm, tol = per_constraint_case()
+    for per_constraint, want_status in ((False, 6), (True, 1)):
+        o = po.Oracle(a["offsets"], a["indices"], a["values"], a["c"], a["var_lb"], a["var_ub"], a["con_lb"], a["con_ub"],
+                      tolerances=tol, per_constraint_residual=per_constraint)
+        o.initialise()
+        cv = o.convergence(x, np.zeros(3))
+        assert cv["l2_primal_residual"] == pytest.approx(0.10630145812734649, rel=1e-14)
+        assert int(cv["status"]) == want_status       # EXPECT_TRUE(status != Optimal) / Optimal
+        if per_constraint:
+            assert o.scalar("linf_relative_primal_residual") == 0.1   # EXPECT_EQ(..., 0.1) in the reference test
+    # through the whole solver: started AT that iterate, the per-constraint run stops before taking a step
+    for per_constraint in (False, True):
+        o = po.Oracle(a["offsets"], a["indices"], a["values"], a["c"], a["var_lb"], a["var_ub"], a["con_lb"], a["con_ub"],
+                      tolerances=tol, per_constraint_residual=per_constraint)
+        o.set_warm_start(warm)
+        assert o.run(-1)
+        assert o.stats().termination_status == 1
+        assert (o.stats().number_of_steps_taken == 0) == per_constraint
+
+
+@pytest.mark.gpu
+def test_gpu_per_constraint_residual_matches_the_reference_test_and_the_oracle():
+    a, x, warm, tol = per_constraint_case()
+    p = gpu_problem(a)
+    for per_constraint in (False, True):
+        o = po.Oracle(a["offsets"], a["indices"], a["values"], a["c"], a["var_lb"], a["var_ub"], a["con_lb"], a["con_ub"],
+                      tolerances=tol, per_constraint_residual=per_constraint)
+        o.set_warm_start(warm)
+        assert o.run(-1)
+        s = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False, per_constraint_residual=per_constraint)
+        for name, v in (("absolute_primal_tolerance", 0.1), ("relative_primal_tolerance", 0.0),
+                        ("absolute_dual_tolerance", 0.1), ("relative_dual_tolerance", 0.0)):
+            s.set(name, v)
+        s.set_warm_start(capi.WarmStart.create(3, 3, warm))
+        sol = capi.solve(p, s)
+        assert sol.return_code == 0, sol.error_string
+        assert sol.termination_status == 1
+        assert sol.stats().number_of_steps_taken == o.stats().number_of_steps_taken
+        assert (sol.stats().number_of_steps_taken == 0) == per_constraint
+        if per_constraint:
+            assert np.array_equal(sol.primal(), x)   # the iterate it was handed, judged optimal row by row
