@@ -27,10 +27,11 @@
 // Summation order: row sums of the SpMVs run left to right in CSR order; vector
 // reductions are chunked (4096 elements per chunk, chunks added left to right),
 // which makes results independent of the OpenMP thread count.
-// Trust-region restart (Methodical1's restart rule, pdlp_restart_strategy.cu:278-364,
-// 983-1678) is not restated: the oracle covers restart_strategy 0 (none) and 1 (KKT),
-// i.e. the Stable1 / Stable2 / Fast1 presets; Methodical1 is covered up to its
-// initial scaling / step size / primal weight (what the reference test pins).
+// Restart strategies: 1 = KKT (Stable1 / Stable2 / Fast1) and 2 = trust region (Methodical1:
+// pdlp_restart_strategy.cu:278-364, 842-1080, 1291-1678, 1681-1900 + utils.cuh:240-345), the
+// latter restated sequentially: a stable sort replaces thrust::sort_by_key (order among equal
+// thresholds only changes rounding of two sums), and gap_reduction_ratio_last_trial, which the
+// reference never initialises (pdlp_restart_strategy.cu:160), starts at 1 as in PDLP.jl.
 // =============================================================================
 #include <algorithm>
 #include <chrono>
@@ -237,6 +238,7 @@ class oracle_t {
   //  last-restart primal, last-restart dual} and 8 scalars {primal weight, step size, total pdlp iterations,
   //  total pdhg iterations, last candidate kkt, last restart kkt, sum of solution weights, iterations since restart}
   double last_linf[2] = {0, 0};  // per-constraint residuals of the last pdlp_oracle_convergence call
+  double gap_reduction_ratio_last_trial = 1.0;  // trust-region restart (see header)
   bool warm_given = false;
   std::vector<double> warm_v[9];
   double warm_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -712,6 +714,188 @@ class oracle_t {
     last_candidate_kkt = cand;
   }
 
+  // ------------------------------------------------ trust-region restart (Methodical1)
+  // localized_duality_gap_container_t: a point, its distances from the last restart and the bounds
+  // on the optimal objective inside the trust region around it.
+  struct local_gap_t {
+    std::vector<double> px, py;
+    double primal_distance = 0, dual_distance = 0, distance = 0;  // squared L2 moves / weighted radius
+    double lower_bound = 0, upper_bound = 0, normalized_gap = 0;
+  };
+  // pdlp_restart_strategy.cu:804-817
+  double weighted_distance(const local_gap_t& g) const
+  {
+    return std::sqrt(g.primal_distance * hp.primal_distance_smoothing * primal_weight +
+                     g.dual_distance * (hp.dual_distance_smoothing / primal_weight));
+  }
+  // :1681-1714 (plain L2 of the difference to the last restart point)
+  void distance_from_last_restart(local_gap_t& g) const
+  {
+    g.primal_distance = reduce_sum(n, [&](int j) { const double d = x_lr[j] - g.px[j]; return d * d; });
+    g.dual_distance   = reduce_sum(m, [&](int i) { const double d = y_lr[i] - g.py[i]; return d * d; });
+    g.distance        = weighted_distance(g);
+  }
+  // bound_optimal_objective (:1034-1051): gradients (:1717-1825), Lagrangian (:1828-1900), trust-region
+  // solve (:1391-1678) on the SCALED problem; radius = g.distance.
+  void bound_optimal_objective(local_gap_t& g)
+  {
+    const int N = n + m;
+    std::vector<double> gp(n), gd(m), sub(m), aty(n);
+    spmv(ATs, g.py.data(), aty.data());
+    for (int j = 0; j < n; ++j) gp[j] = cs[j] - aty[j];  // c - A^T y
+    spmv(As, g.px.data(), gd.data());                   // primal product A x
+    for (int i = 0; i < m; ++i) {                       // compute_subgradient_kernel :1746-1783
+      const double lo = lcs[i], up = ucs[i], prod = gd[i], yi = g.py[i];
+      double sc;
+      if (yi < 0.0) sc = up;
+      else if (yi > 0.0) sc = lo;
+      else if (!std::isfinite(up) && !std::isfinite(lo)) sc = 0.0;
+      else if (!std::isfinite(up) && std::isfinite(lo)) sc = lo;
+      else if (std::isfinite(up) && !std::isfinite(lo)) sc = up;
+      else sc = prod < lo ? lo : (prod > up ? up : prod);
+      sub[i] = sc;
+      gd[i]  = sc - prod;  // dual gradient = subgradient - A x
+    }
+    const double lagrangian = reduce_sum(n, [&](int j) { return g.px[j] * cs[j]; }) -
+                              reduce_sum(n, [&](int j) { return g.px[j] * aty[j]; }) +
+                              reduce_sum(m, [&](int i) { return g.py[i] * sub[i]; });
+    // ---- solve_bound_constrained_trust_region ----
+    std::vector<double> center(N), obj(N), lo(N), up(N), w(N), dir(N, 0.0), thr(N, 0.0);
+    for (int j = 0; j < n; ++j) { center[j] = g.px[j]; obj[j] = gp[j]; lo[j] = ls[j]; up[j] = us[j]; w[j] = 1.0 / tau; }
+    for (int i = 0; i < m; ++i) {
+      center[n + i] = g.py[i];
+      obj[n + i]    = -gd[i];
+      lo[n + i]     = std::isfinite(ucs[i]) ? -INFINITY : 0.0;  // utils.cuh:240-255
+      up[n + i]     = std::isfinite(lcs[i]) ? INFINITY : 0.0;
+      w[n + i]      = 1.0 / sigma;
+    }
+    const double obj_norm = std::sqrt(reduce_sum(N, [&](int k) { return obj[k] * obj[k]; }));
+    std::vector<double> tr(center);
+    if (!(g.distance == 0.0 || obj_norm == 0.0)) {
+      for (int k = 0; k < N; ++k) {  // compute_direction_and_threshold, utils.cuh:291-322
+        if (center[k] >= up[k] && obj[k] <= 0.0) continue;
+        if (center[k] <= lo[k] && obj[k] >= 0.0) continue;
+        if (obj[k] == 0.0) { thr[k] = INFINITY; continue; }
+        dir[k] = -obj[k] / w[k];
+        if (dir[k] > 0.0) thr[k] = (up[k] - center[k]) / dir[k];
+        else if (dir[k] < 0.0) thr[k] = (lo[k] - center[k]) / dir[k];
+      }
+      double high_r2 = 0.0, low_r2 = 0.0;
+      for (int k = 0; k < N; ++k)
+        if (std::isinf(thr[k])) high_r2 += dir[k] * dir[k] * w[k];  // weighted_l2_if_infinite
+      std::vector<int> order(N);
+      for (int k = 0; k < N; ++k) order[k] = k;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return thr[a] < thr[b]; });
+      int range_low = 0, range_high = N;
+      while (range_low < N && thr[order[range_low]] == -INFINITY) ++range_low;
+      for (int k = 0; k < N; ++k)
+        if (thr[order[k]] == INFINITY) { range_high = k; break; }
+      const double target = g.distance;
+      std::vector<double> test(N, 0.0);
+      auto sthr = [&](int k) { return thr[order[k]]; };
+      while (range_low != range_high) {  // solve_bound_constrained_trust_region_kernel :1291-1358
+        const int size = range_high - range_low;
+        const double t = (size & 1) == 0 ? 0.5 * (sthr(range_low + size / 2 - 1) + sthr(range_low + size / 2))
+                                         : sthr(range_low + size / 2);
+        double test_r2 = 0.0;
+        for (int k = range_low; k < range_high; ++k) {
+          const int q = order[k];
+          test[k]     = std::min(std::max(center[q] + t * dir[q], lo[q]), up[q]);
+          const double d = test[k] - center[q];
+          test_r2 += d * d * w[q];
+        }
+        const bool too_high = low_r2 + test_r2 + (t * t) * high_r2 >= target * target;
+        if (too_high) {
+          int new_high = range_high;
+          for (int k = range_low; k < range_high; ++k)
+            if (sthr(k) >= t) { new_high = k; break; }
+          for (int k = new_high; k < range_high; ++k) high_r2 += dir[order[k]] * dir[order[k]] * w[order[k]];
+          range_high = new_high;
+        } else {
+          int new_low = range_low;
+          for (int k = range_high - 1; k >= range_low; --k)
+            if (sthr(k) <= t) { new_low = k + 1; break; }
+          for (int k = range_low; k < new_low; ++k) {
+            const double d = test[k] - center[order[k]];
+            low_r2 += d * d * w[order[k]];
+          }
+          range_low = new_low;
+        }
+      }
+      double target_threshold;  // target_threshold_determination_kernel :1081-1100
+      if (high_r2 <= 0.0) target_threshold = *std::max_element(thr.begin(), thr.end());
+      else target_threshold = std::sqrt((target * target - low_r2) / high_r2);
+      for (int k = 0; k < N; ++k) {
+        // a component that does not move keeps its value (inf * 0 would be NaN in the reference's a + t * b)
+        const double moved = dir[k] == 0.0 ? center[k] : center[k] + target_threshold * dir[k];
+        tr[k]              = std::min(std::max(moved, lo[k]), up[k]);
+      }
+    }
+    // compute_bound :1053-1078
+    g.lower_bound = lagrangian + reduce_sum(n, [&](int j) { return (tr[j] - g.px[j]) * gp[j]; });
+    g.upper_bound = lagrangian + reduce_sum(m, [&](int i) { return (tr[n + i] - g.py[i]) * gd[i]; });
+  }
+
+  // pdlp_restart_strategy.cu:278-364
+  void run_trust_region_restart(trace_row_t& tr)
+  {
+    if (its_since_restart == 0) return;
+    bool restart = should_do_artificial_restart(k_total);
+    // compute_localized_duality_gaps :983-1031
+    local_gap_t avg, cur;
+    avg.px = x_avg; avg.py = y_avg;
+    cur.px = x;     cur.py = y;
+    distance_from_last_restart(avg);
+    distance_from_last_restart(cur);
+    bound_optimal_objective(avg);
+    bound_optimal_objective(cur);
+    avg.normalized_gap = (avg.upper_bound - avg.lower_bound) / avg.distance;
+    cur.normalized_gap = (cur.upper_bound - cur.lower_bound) / cur.distance;
+    // pick_restart_candidate :842-873
+    const bool to_avg = cur.normalized_gap / cur.distance >= avg.normalized_gap / avg.distance;
+    local_gap_t& cand = to_avg ? avg : cur;
+    if (!restart) {  // should_do_adaptive_restart_normalized_duality_gap :903-937
+      local_gap_t last;
+      last.px = x_lr; last.py = y_lr;
+      last.primal_distance = cand.primal_distance;  // only the radius is taken from the candidate (:921-926)
+      last.dual_distance   = cand.dual_distance;
+      last.distance        = weighted_distance(cand);
+      bound_optimal_objective(last);
+      last.normalized_gap = (last.upper_bound - last.lower_bound) / last.distance;
+      const double ratio  = cand.normalized_gap / last.normalized_gap;
+      if (ratio < hp.necessary_reduction_for_restart &&
+          (ratio < hp.sufficient_reduction_for_restart || ratio > gap_reduction_ratio_last_trial))
+        restart = true;
+      gap_reduction_ratio_last_trial = ratio;
+    }
+    if (!restart) return;
+    const bool use_avg = to_avg && !hp.never_restart_to_average;
+    if (use_avg) { x = cand.px; y = cand.py; }
+    last_restart_was_average = use_avg;
+    auto new_primal_weight = [&]() {  // :685-732
+      const double pd = std::sqrt(cand.primal_distance), dd = std::sqrt(cand.dual_distance);
+      const double guard = 1.0e-10;
+      if (pd < guard || pd >= 1.0 / guard || dd < guard || dd >= 1.0 / guard) return;
+      const double lw = hp.primal_weight_update_smoothing * std::log(dd / pd) +
+                        (1.0 - hp.primal_weight_update_smoothing) * std::log(primal_weight);
+      primal_weight = std::exp(lw);
+      tau           = step_size / primal_weight;
+      sigma         = step_size * primal_weight;
+    };
+    // :341-349 — both orders store the candidate as the new restart point; the weight only feeds the stored radius,
+    // which the next call recomputes
+    x_lr = cand.px;
+    y_lr = cand.py;
+    new_primal_weight();
+    std::fill(sum_x.begin(), sum_x.end(), 0.0);
+    std::fill(sum_y.begin(), sum_y.end(), 0.0);
+    sum_w             = 0.0;
+    its_since_restart = 0;
+    n_restarts += 1;
+    tr.restarted  = 1;
+    tr.to_average = use_avg ? 1 : 0;
+  }
+
   // -------------------------------------------------------- outer loop
   // pdlp.cu:1081-1185.  Runs until termination or until `max_accepted_steps` more PDLP iterations
   // have been taken (used by the step-by-step parity tests).  Returns true when a solution was filled.
@@ -761,6 +945,7 @@ class oracle_t {
           scale_solutions(x, y);
         }
         if (hp.restart_strategy == 1) run_kkt_restart(tr);
+        else if (hp.restart_strategy == 2) run_trust_region_restart(tr);
         if (!hp.rescale_for_restart) scale_solutions(x, y);  // :1168-1175
         trace.push_back(tr);
       }

@@ -93,7 +93,28 @@ def test_objective_matches_reference_dual_simplex(simplex_golden, rel, tol, otol
     assert r["dual_objective"] == pytest.approx(want["objective"], rel=otol, abs=otol)
 
 
-@pytest.mark.parametrize("mode", [po.STABLE1, po.STABLE2, po.FAST1])
+def test_methodical1_very_low_tolerance_afiro():
+    """python/cuopt/cuopt/tests/linear_programming/test_lp_solver.py:101-121 (test_very_low_tolerance): Methodical1
+    (trust-region restart), optimality tolerance 1e-12, no infeasibility detection -> Optimal, objective -464.7531."""
+    o, _ = oracle_for("linear_programming/afiro_original.mps", mode=po.METHODICAL1, tol=1e-12, iteration_limit=2000000)
+    r = o.solve()
+    assert r["status"] == "Optimal"
+    assert r["primal_objective"] == pytest.approx(-464.7531)          # the reference's assertion (rel 1e-6)
+    assert r["primal_objective"] == pytest.approx(-464.75314285714285, rel=1e-10)
+    assert o.stats().n_restarts >= 1                                  # the trust-region rule did fire
+
+
+@pytest.mark.parametrize("rel,tol,otol", [c for c in SIMPLEX_CASES if "minrep" not in c[0]])
+def test_methodical1_objective_matches_reference_dual_simplex(simplex_golden, rel, tol, otol):
+    want = simplex_golden[rel]
+    o, _ = oracle_for(rel, mode=po.METHODICAL1, tol=tol, iteration_limit=400000)
+    r = o.solve()
+    assert r["status"] == "Optimal", r
+    assert r["primal_objective"] == pytest.approx(want["objective"], rel=otol, abs=otol)
+    assert r["dual_objective"] == pytest.approx(want["objective"], rel=otol, abs=otol)
+
+
+@pytest.mark.parametrize("mode", [po.STABLE1, po.STABLE2, po.FAST1, po.METHODICAL1])
 def test_presets_converge_on_afiro(mode):
     o, _ = oracle_for("linear_programming/afiro_original.mps", mode=mode, tol=1e-8, iteration_limit=200000)
     r = o.solve()
