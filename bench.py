@@ -290,6 +290,13 @@ def main():
                                "frac_of_hbm_peak": b_iter / (prof.ms_iteration * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                  "grids": {"primal": prof.grid_primal, "dual": prof.grid_dual, "transpose": prof.grid_transpose},
                  "setup_seconds_per_step": setup_s / args.steps, "time_to_gap": to_gap}
+    if rank == 0 and args.workload == "c3":
+        # the reference's own CPU path on this LP (dual simplex, 1 core), from the committed fixture — not re-timed here
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "c3_reference_simplex.json")) as f:
+                extra["reference_dual_simplex"] = [c for c in json.load(f)["cases"] if c["rows"] == lp.m][0]
+        except Exception:  # noqa: BLE001
+            pass
     if rank == 0:
         extra["solver_seconds_per_step"] = {"pdhg_batches": loop_s / args.steps, "major_iterations": term_s / args.steps}
         extra["transport"] = os.environ.get("CUOPT_B200_DIST_MODE", "p2p") if world > 1 else None

@@ -139,3 +139,20 @@ def test_warm_start_style_additivity_of_stepping():
     a.run(25); a.run(15)
     b.run(40)
     assert np.array_equal(a.vector("x"), b.vector("x")) and a.scalar("step_size") == b.scalar("step_size")
+
+
+def test_pds_shaped_lp_against_reference_dual_simplex():
+    """configs[2] shape (multicommodity flow, synthesised): the oracle's PDLP against the optimal objective the
+    reference's own CPU dual simplex found (tests/golden/c3_reference_simplex.json, scripts/gen_golden_c3.py)."""
+    import json
+    import os
+    from cuopt_b200 import lpgen
+    with open(os.path.join(os.path.dirname(__file__), "golden", "c3_reference_simplex.json")) as f:
+        case = json.load(f)["cases"][0]
+    lp = lpgen.multicommodity(nodes=case["nodes"], arcs=case["arcs"], commodities=11, seed=1234)
+    assert (lp.m, lp.n, lp.nnz) == (case["rows"], case["cols"], case["nnz"])
+    o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=1e-6)
+    assert o.run(-1)
+    assert o.stats().termination_status == 1
+    assert o.stats().primal_objective == pytest.approx(case["objective"], rel=1e-5)
+    assert o.stats().dual_objective == pytest.approx(case["objective"], rel=1e-5)
