@@ -33,6 +33,34 @@ UNIT = "iterations/s"
 ITERS_PER_STEP = 2000
 
 
+def usable_cores() -> int:
+    """Host cores this process may really use: min(cpu_count, affinity mask, cgroup CPU quota).  A container that shows
+    128 CPUs but is throttled to a few makes a 128-thread OpenMP run slower than an 8-thread one (measured: 2.1 vs 4.7
+    iterations/s on the 10M LP), so the CPU legs size their thread pool with this."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:  # noqa: BLE001
+        pass
+    for path, parse in (("/sys/fs/cgroup/cpu.max", lambda t: t.split()),
+                        ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", None)):
+        try:
+            with open(path) as f:
+                txt = f.read().strip()
+            if parse:
+                quota, period = parse(txt)
+                if quota != "max":
+                    n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+            else:
+                with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                    period = float(f.read().strip())
+                if float(txt) > 0:
+                    n = min(n, max(1, int(float(txt) / period + 0.5)))
+        except Exception:  # noqa: BLE001
+            pass
+    return max(1, min(n, 64))  # beyond ~64 threads the memory-bound CPU SpMV stops scaling
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -119,13 +147,15 @@ def config_dict(args, lp, n_gpus):
 
 def run_reference(args):
     """CPU arm: the reference's PDLP as restated by the oracle port, all host threads, bounded sample."""
-    from oracle import pdlp_oracle as po
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = usable_cores()
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun presets 1; must be set before the OpenMP runtime starts
+    from oracle import pdlp_oracle as po
     lp = workload(args)
-    cores = os.cpu_count() or 1
-    o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=0.0)
+    o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=0.0,
+                  num_threads=cores)
     o.initialise()
     sample = args.cpu_iters
     for _ in range(args.warmup):
@@ -301,11 +331,14 @@ def main():
         extra["solver_seconds_per_step"] = {"pdhg_batches": loop_s / args.steps, "major_iterations": term_s / args.steps}
         extra["transport"] = os.environ.get("CUOPT_B200_DIST_MODE", "p2p") if world > 1 else None
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
+            cores = usable_cores()
+            os.environ["OMP_NUM_THREADS"] = str(cores)
             from oracle import pdlp_oracle as po
-            o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=0.0)
+            o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=0.0,
+                          num_threads=cores)
             o.initialise(); o.run(5)
             tc = time.perf_counter(); o.run(args.cpu_iters * 3); tc = time.perf_counter() - tc
-            cpu = {"value": args.cpu_iters * 3 / tc, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            cpu = {"value": args.cpu_iters * 3 / tc, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{args.cpu_iters * 3} PDLP iterations of the same LP by oracle/pdlp_oracle.cpp (OpenMP)"}
 
     if rank == 0:

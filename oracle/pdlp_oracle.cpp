@@ -33,6 +33,9 @@
 // thresholds only changes rounding of two sums), and gap_reduction_ratio_last_trial, which the
 // reference never initialises (pdlp_restart_strategy.cu:160), starts at 1 as in PDLP.jl.
 // =============================================================================
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -967,6 +970,9 @@ void* pdlp_oracle_create(int m, int n, const int* off, const int* idx, const dou
                          const double* l, const double* u, const double* lc, const double* uc, int maximize,
                          double objective_offset, const hyper_t* hp, const settings_t* st)
 {
+#ifdef _OPENMP
+  if (st->num_threads > 0) omp_set_num_threads(st->num_threads);  // results do not depend on it (chunked reductions)
+#endif
   return new oracle_t(m, n, off, idx, val, c, l, u, lc, uc, maximize, objective_offset, *hp, *st);
 }
 void pdlp_oracle_destroy(void* h) { delete static_cast<oracle_t*>(h); }

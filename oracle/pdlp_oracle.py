@@ -169,7 +169,8 @@ class Oracle:
 
     def __init__(self, offsets, indices, values, c, var_lb, var_ub, con_lb, con_ub, *, maximize=False,
                  objective_offset=0.0, mode=STABLE2, hyper: Hyper | None = None, tol=1e-4, iteration_limit=2**31 - 1,
-                 time_limit=float("inf"), tolerances: dict | None = None, per_constraint_residual=False):
+                 time_limit=float("inf"), tolerances: dict | None = None, per_constraint_residual=False,
+                 num_threads: int = 0):
         L = lib()
         self.m, self.n = len(con_lb), len(c)
         self._keep = [np.ascontiguousarray(offsets, np.int32), np.ascontiguousarray(indices, np.int32)] + [
@@ -179,7 +180,8 @@ class Oracle:
                  rel_gap_tol=tol)
         if tolerances:
             t.update(tolerances)
-        self.settings = Settings(iteration_limit=int(iteration_limit), time_limit=float(time_limit), num_threads=0,
+        self.settings = Settings(iteration_limit=int(iteration_limit), time_limit=float(time_limit),
+                                 num_threads=int(num_threads),
                                  per_constraint_residual=int(bool(per_constraint_residual)), **t)
         k = self._keep
         self.h = C.c_void_p(L.pdlp_oracle_create(
