@@ -86,6 +86,9 @@ struct settings_t {
   double time_limit;
   int num_threads;
   int per_constraint_residual;  // convergence_information.cu:163-204, termination_strategy.cu:141-166
+  int detect_infeasibility;     // infeasibility_information.cu, termination_strategy.cu:229-250, pdlp.cu:716-770
+  int strict_infeasibility;
+  double primal_infeasible_tol, dual_infeasible_tol;
 };
 
 struct stats_t {
@@ -195,6 +198,8 @@ inline double div_check_zero(double a, double b) { return b == 0.0 ? 0.0 : a / b
 struct convergence_t {  // termination_strategy/convergence_information.cu
   double l2_primal_residual = 0, l2_dual_residual = 0, primal_objective = 0, dual_objective = 0;
   double linf_relative_primal_residual = 0, linf_relative_dual_residual = 0;  // per_constraint_residual only
+  double max_primal_ray_infeasibility = 0, primal_ray_linear_objective = 0;   // detect_infeasibility only
+  double max_dual_ray_infeasibility = 0, dual_ray_linear_objective = 0;
   double gap = 0, abs_objective = 0, l2_primal_variable = 0, l2_dual_variable = 0;
   std::vector<double> reduced_cost;
   int status = 6;
@@ -574,6 +579,70 @@ class oracle_t {
     }
     if (dual_feas && primal_feas && optimal_gap) cv.status = 1;
     else if (primal_feas) cv.status = 7;
+    else if (st.detect_infeasibility) {
+      infeasibility_information(px, py, cv);
+      // termination_strategy.cu:229-250 (2 = Infeasible, 3 = Unbounded in constants.h:62-72)
+      if (cv.dual_ray_linear_objective > 0.0 &&
+          cv.max_dual_ray_infeasibility / cv.dual_ray_linear_objective <= st.primal_infeasible_tol)
+        cv.status = 2;
+      else if (cv.primal_ray_linear_objective < 0.0 &&
+               cv.max_primal_ray_infeasibility / -cv.primal_ray_linear_objective <= st.dual_infeasible_tol)
+        cv.status = 3;
+    }
+  }
+
+  // infeasibility_information.cu:183-223 (the iterate itself is the ray estimate) on the UNSCALED problem.
+  // tmp_m holds A px, tmp_n holds c - A^T py from compute_convergence_information above.
+  void infeasibility_information(const std::vector<double>& px, const std::vector<double>& py, convergence_t& cv)
+  {
+    double xinf = 0.0, yinf = 0.0;
+    for (int j = 0; j < n; ++j) xinf = std::max(xinf, std::fabs(px[j]));
+    for (int i = 0; i < m; ++i) yinf = std::max(yinf, std::fabs(py[i]));
+    const double xinv = xinf != 0.0 ? 1.0 / xinf : 0.0;  // eltwiseDivideCheckZero
+    // homogeneous primal residual (:226-248): A x against the bounds with every finite bound replaced by 0
+    double hres = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const double hl = std::isfinite(lc[i]) ? 0.0 : lc[i], hu = std::isfinite(uc[i]) ? 0.0 : uc[i];
+      hres = std::max(hres, std::fabs(violation(tmp_m[i], hl, hu)));
+    }
+    double max_viol = 0.0;  // compute_max_violation :250-268, utils.cuh:181-193
+    for (int j = 0; j < n; ++j) {
+      if (std::isfinite(l[j])) max_viol = std::max(max_viol, -px[j]);
+      if (std::isfinite(u[j])) max_viol = std::max(max_viol, px[j]);
+    }
+    double pobj = reduce_sum(n, [&](int j) { return px[j] * c[j]; }) * xinv;  // :270-287
+    // homogeneous dual residual (:289-313): gradient -A^T y, its reduced costs with the iterate as the ray
+    std::vector<double> rc(n);
+    double hdres = 0.0, rcinf = 0.0;
+    for (int j = 0; j < n; ++j) {
+      const double g = (tmp_n[j] - c[j]);  // tmp_n = c - A^T y  =>  -A^T y
+      const double bound_value = g > 0.0 ? l[j] : u[j];
+      double r;
+      if (hp.handle_some_primal_gradients_on_finite_bounds_as_residuals) {
+        if (g == 0.0) r = g;
+        else if (std::fabs(px[j] - bound_value) <= std::fabs(px[j])) r = g;
+        else r = 0.0;
+      } else {
+        if (g == 0.0) r = g;
+        else if (std::isfinite(bound_value)) r = g;
+        else r = 0.0;
+      }
+      rc[j] = r;
+      hdres = std::max(hdres, std::fabs(g - r));
+      rcinf = std::max(rcinf, std::fabs(r));
+    }
+    double dobj = reduce_sum(m, [&](int i) { return bound_value_reduced_cost_product(py[i], lc[i], uc[i]); }) +
+                  reduce_sum(n, [&](int j) { return bound_value_reduced_cost_product(rc[j], l[j], u[j]); });
+    // compute_remaining_stats_kernel :118-181
+    const double scaling = std::max(yinf, rcinf);
+    if (scaling != 0.0) { hdres /= scaling; dobj /= scaling; } else { hdres = 0.0; dobj = 0.0; }
+    double max_primal;
+    if (xinf > 0.0) max_primal = std::max(hres, max_viol) / xinf;
+    else { max_primal = 0.0; pobj = 0.0; }
+    cv.max_primal_ray_infeasibility = max_primal;
+    cv.primal_ray_linear_objective  = pobj;
+    cv.max_dual_ray_infeasibility   = hdres;
+    cv.dual_ray_linear_objective    = dobj;
   }
 
   // pdlp_restart_strategy.cu:367-405
@@ -637,6 +706,18 @@ class oracle_t {
     }
     if (avg_opt) { fill_solution(x_avg, y_avg, conv_avg, 1, true); return true; }   // :685-700
     if (cur_opt) { fill_solution(x, y, conv_cur, 1, false); return true; }          // :701-716
+    // pdlp.cu:716-770: infeasibility.  strict: any of the two iterates suffices; else both must agree
+    {
+      const int sc = conv_cur.status, sa = conv_avg.status;
+      const bool ic = sc == 2 || sc == 3, ia = sa == 2 || sa == 3;
+      if (st.strict_infeasibility) {
+        if (ic) { fill_solution(x, y, conv_cur, sc, false); return true; }
+        if (ia) { fill_solution(x_avg, y_avg, conv_avg, sa, true); return true; }
+      } else if (ic && sc == sa) {
+        fill_solution(x, y, conv_cur, sc, false);
+        return true;
+      }
+    }
     if (valid_step_size == -1) {  // :780-789: error solution (empty vectors)
       result                    = stats_t{};
       result.termination_status = 6;

@@ -54,7 +54,8 @@ class Settings(C.Structure):
         ("abs_primal_tol", C.c_double), ("rel_primal_tol", C.c_double),
         ("abs_gap_tol", C.c_double), ("rel_gap_tol", C.c_double),
         ("iteration_limit", C.c_int), ("time_limit", C.c_double), ("num_threads", C.c_int),
-        ("per_constraint_residual", C.c_int),
+        ("per_constraint_residual", C.c_int), ("detect_infeasibility", C.c_int), ("strict_infeasibility", C.c_int),
+        ("primal_infeasible_tol", C.c_double), ("dual_infeasible_tol", C.c_double),
     ]
 
 
@@ -170,7 +171,8 @@ class Oracle:
     def __init__(self, offsets, indices, values, c, var_lb, var_ub, con_lb, con_ub, *, maximize=False,
                  objective_offset=0.0, mode=STABLE2, hyper: Hyper | None = None, tol=1e-4, iteration_limit=2**31 - 1,
                  time_limit=float("inf"), tolerances: dict | None = None, per_constraint_residual=False,
-                 num_threads: int = 0):
+                 num_threads: int = 0, detect_infeasibility=False, strict_infeasibility=False,
+                 primal_infeasible_tol=1e-8, dual_infeasible_tol=1e-8):
         L = lib()
         self.m, self.n = len(con_lb), len(c)
         self._keep = [np.ascontiguousarray(offsets, np.int32), np.ascontiguousarray(indices, np.int32)] + [
@@ -181,7 +183,10 @@ class Oracle:
         if tolerances:
             t.update(tolerances)
         self.settings = Settings(iteration_limit=int(iteration_limit), time_limit=float(time_limit),
-                                 num_threads=int(num_threads),
+                                 num_threads=int(num_threads), detect_infeasibility=int(bool(detect_infeasibility)),
+                                 strict_infeasibility=int(bool(strict_infeasibility)),
+                                 primal_infeasible_tol=float(primal_infeasible_tol),
+                                 dual_infeasible_tol=float(dual_infeasible_tol),
                                  per_constraint_residual=int(bool(per_constraint_residual)), **t)
         k = self._keep
         self.h = C.c_void_p(L.pdlp_oracle_create(

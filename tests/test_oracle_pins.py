@@ -156,3 +156,47 @@ def test_pds_shaped_lp_against_reference_dual_simplex():
     assert o.stats().termination_status == 1
     assert o.stats().primal_objective == pytest.approx(case["objective"], rel=1e-5)
     assert o.stats().dual_objective == pytest.approx(case["objective"], rel=1e-5)
+
+
+# ------------------------------------------------------------------ infeasibility detection (oracle only so far)
+def c_api_infeasible_lp():
+    """The LP of the reference's test_infeasible_problem (cpp/tests/linear_programming/c_api_tests/c_api_test.c:625-700)."""
+    inf = np.inf
+    off = np.array([0, 2, 4, 6, 7, 9, 10, 12, 15, 17], np.int32)
+    idx = np.array([0, 1, 0, 1, 0, 1, 3, 2, 3, 2, 0, 3, 0, 1, 2, 1, 2], np.int32)
+    val = np.array([-0.5, 1.0, 2.0, -1.0, 3.0, 1.0, 1.0, 3.0, -1.0, 1.0, 1.0, 1.0, 1.0, 2.0, 1.0, 1.0, 1.0])
+    rhs = np.array([0.5, 3.0, 6.0, 2.0, 2.0, 5.0, 10.0, 14.0, 1.0])
+    sense = "GGLLLGLLG"
+    lc = np.array([r if s in "GE" else -inf for r, s in zip(rhs, sense)])
+    uc = np.array([r if s in "LE" else inf for r, s in zip(rhs, sense)])
+    return off, idx, val, np.zeros(4), np.zeros(4), np.full(4, inf), lc, uc
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_infeasibility_detection_on_the_reference_c_api_infeasible_lp(strict):
+    off, idx, val, c, l, u, lc, uc = c_api_infeasible_lp()
+    # the reference's own verdict on it (its test expects CUOPT_TERIMINATION_STATUS_INFEASIBLE from the dual simplex)
+    from oracle import ref_cpu
+    if ref_cpu.available():
+        assert ref_cpu.dual_simplex(off, idx, val, lc, uc, c, l, u)["status"] == "INFEASIBLE"
+    o = po.Oracle(off, idx, val, c, l, u, lc, uc, tol=1e-4, detect_infeasibility=True, strict_infeasibility=strict,
+                  iteration_limit=100000)
+    assert o.run(-1)
+    assert o.stats().termination_status == 2   # PrimalInfeasible == CUOPT_TERIMINATION_STATUS_INFEASIBLE
+    # without detection PDLP cannot say so: it runs into its limit
+    o = po.Oracle(off, idx, val, c, l, u, lc, uc, tol=1e-4, iteration_limit=2000)
+    assert o.run(-1)
+    assert o.stats().termination_status == 4
+
+
+def test_infeasibility_detection_flags_an_unbounded_lp():
+    # min -x  s.t.  x - y = 0,  x, y >= 0: the ray (1, 1) improves forever
+    inf = np.inf
+    off, idx, val = np.array([0, 2], np.int32), np.array([0, 1], np.int32), np.array([1.0, -1.0])
+    args = (off, idx, val, np.array([-1.0, 0.0]), np.zeros(2), np.full(2, inf), np.zeros(1), np.zeros(1))
+    from oracle import ref_cpu
+    if ref_cpu.available():
+        assert ref_cpu.dual_simplex(off, idx, val, args[6], args[7], args[3], args[4], args[5])["status"] == "UNBOUNDED"
+    o = po.Oracle(*args, tol=1e-4, detect_infeasibility=True, strict_infeasibility=True, iteration_limit=100000)
+    assert o.run(-1)
+    assert o.stats().termination_status == 3   # DualInfeasible == CUOPT_TERIMINATION_STATUS_UNBOUNDED
