@@ -384,8 +384,16 @@ cuopt_int_t cuOptSolve(cuOptOptimizationProblem problem, cuOptSolverSettings set
     h->sol.error_status  = CUOPT_VALIDATION_ERROR;
     h->sol.error_message = "cuopt-b200 implements the LP (PDLP) path only; the problem declares integer variables";
   } else {
-    // method Concurrent / DualSimplex / PDLP all run PDLP here; crossover is not part of this build
-    h->sol = solve_lp(p, ss.pdlp());
+    // method Concurrent / DualSimplex / PDLP all run PDLP here; crossover is not part of this build.  A caller who
+    // asks for the dual simplex explicitly gets what that method would tell apart — infeasible / unbounded LPs (the
+    // reference's test_infeasible_problem asks exactly that of CUOPT_METHOD_DUAL_SIMPLEX): PDLP stands in with its
+    // infeasibility detection switched on.  Concurrent (the default) keeps the caller's infeasibility_detection.
+    pdlp_settings_t run = ss.pdlp();
+    if (run.method == 2 /* CUOPT_METHOD_DUAL_SIMPLEX */) {
+      run.detect_infeasibility = true;
+      run.strict_infeasibility = true;
+    }
+    h->sol = solve_lp(p, run);
     if (h->sol.error_status == 0) log_solution(ss.pdlp(), p, h->sol);
   }
   *solution_ptr = h;

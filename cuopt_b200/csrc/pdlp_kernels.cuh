@@ -67,6 +67,7 @@ struct eval_consts_t {
   double l2_norm_b, l2_norm_c;
   int reduced_cost_rule;  // 1: handle_some_primal_gradients_on_finite_bounds_as_residuals
   int per_constraint_residual;  // feasibility tests on linf(residual_i - rel * rhs_i) <= abs (termination_strategy.cu:141-166)
+  double primal_infeasible_tol, dual_infeasible_tol;  // infeasibility detection (k_infeasibility_* below)
 };
 
 // Publish per-CTA partial sums and elect the last CTA to finish (returns true in every thread of
@@ -1031,6 +1032,147 @@ __global__ void __launch_bounds__(EW_THREADS) k_eval_cols_from_aty(pdhg_ctl_t* _
   }
   if (!publish_and_elect<8>(acc, parts, &ctl->ticket[1], red)) return;
   eval_finalize(ctl, parts, parts_rows, n_parts_rows, k, out, red, parts_max, max_rows, n_max_rows);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Infeasibility detection (termination_strategy/infeasibility_information.cu:183-223, termination_strategy.cu:229-250):
+// the iterate itself is the ray estimate.  Two element-wise passes over the products the evaluation already formed
+// (A x and A^T y for the current and the average iterate), launched only when `infeasibility_detection` is set; the
+// last CTA of the column pass turns a "keep going" status of k_eval_cols_from_aty into 2 (PrimalInfeasible) or
+// 3 (DualInfeasible).
+// rows -> parts (6 x gridDim.x): max |violation(Ax; homogeneous bounds)|, max |y|, sum bound_value_product(y) x {cur, avg}
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) k_infeasibility_rows(int m,
+                                                                   const double* __restrict__ ax_cur,
+                                                                   const double* __restrict__ ax_avg,
+                                                                   const double* __restrict__ y_cur,
+                                                                   const double* __restrict__ y_avg,
+                                                                   const double* __restrict__ lc,
+                                                                   const double* __restrict__ uc,
+                                                                   double* __restrict__ parts)
+{
+  __shared__ double red[32];
+  double hres[2] = {0, 0}, yinf[2] = {0, 0}, dobj[2] = {0, 0};
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const double lo = lc[i], hi = uc[i];
+    const double hl = isfinite(lo) ? 0.0 : lo, hu = isfinite(hi) ? 0.0 : hi;  // zero_if_is_finite, utils.cuh:256-263
+    const double s[2]  = {ax_cur[i], ax_avg[i]};
+    const double yv[2] = {y_cur[i], y_avg[i]};
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const double viol = s[v] < hl ? hl - s[v] : (s[v] > hu ? s[v] - hu : 0.0);
+      hres[v] = fmax(hres[v], fabs(viol));
+      yinf[v] = fmax(yinf[v], fabs(yv[v]));
+      dobj[v] += bound_value_product(yv[v], lo, hi);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const double a = block_reduce<true>(hres[v], red);
+    const double b = block_reduce<true>(yinf[v], red);
+    const double c = block_reduce(dobj[v], red);
+    if (threadIdx.x == 0) {
+      parts[(0 + v) * gridDim.x + blockIdx.x] = a;
+      parts[(2 + v) * gridDim.x + blockIdx.x] = b;
+      parts[(4 + v) * gridDim.x + blockIdx.x] = c;
+    }
+  }
+}
+// columns -> parts (12 x gridDim.x): max |x|, max bound violation of the ray, max |g - rc|, max |rc| (max), c.x,
+// sum bound_value_product(rc) (sum), each x {cur, avg}; g = -A^T y.  Last CTA: compute_remaining_stats_kernel
+// (:118-181) + the two tests.
+__global__ void __launch_bounds__(EW_THREADS) k_infeasibility_cols(pdhg_ctl_t* __restrict__ ctl,
+                                                                   int n,
+                                                                   const double* __restrict__ aty_cur,
+                                                                   const double* __restrict__ aty_avg,
+                                                                   const double* __restrict__ x_cur,
+                                                                   const double* __restrict__ x_avg,
+                                                                   const double* __restrict__ c,
+                                                                   const double* __restrict__ l,
+                                                                   const double* __restrict__ u,
+                                                                   double* __restrict__ parts,
+                                                                   const double* __restrict__ parts_rows,
+                                                                   int n_parts_rows,
+                                                                   eval_consts_t k,
+                                                                   eval_t* __restrict__ out)
+{
+  __shared__ double red[32];
+  __shared__ bool is_last;
+  double mx[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // xinf, max_viol, hdres, rcinf  x {cur, avg}
+  double sm[4] = {0, 0, 0, 0};              // c.x, dobj_rc            x {cur, avg}
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double lo = l[j], hi = u[j], cj = c[j];
+    const double s[2]  = {aty_cur[j], aty_avg[j]};
+    const double xv[2] = {x_cur[j], x_avg[j]};
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      mx[0 + v] = fmax(mx[0 + v], fabs(xv[v]));
+      if (isfinite(lo)) mx[2 + v] = fmax(mx[2 + v], -xv[v]);  // utils.cuh:181-193
+      if (isfinite(hi)) mx[2 + v] = fmax(mx[2 + v], xv[v]);
+      const double g     = -s[v];
+      const double bound = g > 0.0 ? lo : hi;
+      double rc;
+      if (g == 0.0) rc = g;
+      else if (k.reduced_cost_rule ? (fabs(xv[v] - bound) <= fabs(xv[v])) : isfinite(bound)) rc = g;
+      else rc = 0.0;
+      mx[4 + v] = fmax(mx[4 + v], fabs(g - rc));
+      mx[6 + v] = fmax(mx[6 + v], fabs(rc));
+      sm[0 + v] += xv[v] * cj;
+      sm[2 + v] += bound_value_product(rc, lo, hi);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const double t = block_reduce<true>(mx[q], red);
+    if (threadIdx.x == 0) parts[q * gridDim.x + blockIdx.x] = t;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double t = block_reduce(sm[q], red);
+    if (threadIdx.x == 0) parts[(8 + q) * gridDim.x + blockIdx.x] = t;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(&ctl->ticket[3], 1u);
+    is_last          = (t == gridDim.x - 1);
+    if (is_last) ctl->ticket[3] = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double cmax[8], csum[4], rmax[4], rsum[2];
+  for (int q = 0; q < 8; ++q) cmax[q] = gather_partials_max(parts + q * gridDim.x, gridDim.x, red);
+  for (int q = 0; q < 4; ++q) csum[q] = gather_partials(parts + (8 + q) * gridDim.x, gridDim.x, red);
+  for (int q = 0; q < 4; ++q) rmax[q] = gather_partials_max(parts_rows + q * n_parts_rows, n_parts_rows, red);
+  for (int q = 0; q < 2; ++q) rsum[q] = gather_partials(parts_rows + (4 + q) * n_parts_rows, n_parts_rows, red);
+  if (threadIdx.x != 0) return;
+  for (int v = 0; v < 2; ++v) {
+    if (out[v].status != 6) continue;  // Optimal / PrimalFeasible were decided first (termination_strategy.cu:141-227)
+    const double xinf = cmax[0 + v], max_viol = cmax[2 + v], rcinf = cmax[6 + v];
+    const double hres = rmax[0 + v], yinf = rmax[2 + v];
+    double hdres = cmax[4 + v];
+    double pobj  = xinf != 0.0 ? csum[0 + v] * (1.0 / xinf) : 0.0;
+    double dobj  = rsum[v] + csum[2 + v];
+    const double scaling = fmax(yinf, rcinf);
+    if (scaling != 0.0) {
+      hdres /= scaling;
+      dobj /= scaling;
+    } else {
+      hdres = 0.0;
+      dobj  = 0.0;
+    }
+    double max_primal;
+    if (xinf > 0.0) {
+      max_primal = fmax(hres, max_viol) / xinf;
+    } else {
+      max_primal = 0.0;
+      pobj       = 0.0;
+    }
+    if (dobj > 0.0 && hdres / dobj <= k.primal_infeasible_tol) out[v].status = 2;
+    else if (pobj < 0.0 && max_primal / -pobj <= k.dual_infeasible_tol) out[v].status = 3;
+  }
 }
 
 // Averages + in-place unscaling ahead of the evaluation (pdlp.cu:1103-1136,

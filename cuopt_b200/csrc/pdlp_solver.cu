@@ -256,6 +256,7 @@ struct pdlp_solver_t::impl_t {
   bool eval_tma = false;
   dvec<double> eval_m, eval_n;  // A x (current, average) and, on one GPU, A^T y (current, average)
   dvec<double> part_max;        // per_constraint_residual: per-CTA maxima, rows (2 x grid_m) then columns (2 x grid_n)
+  dvec<double> part_infeas;     // infeasibility detection: rows (6 x grid_m) then columns (12 x grid_n)
   // gather blocking (pdlp_kernels.cuh): the scaled A / A^T cut into column blocks whose slice of the gathered vector
   // is L2-sized; B == 1 (small LPs) keeps the fused kernels
   struct gather_blocks_t {
@@ -426,6 +427,12 @@ struct pdlp_solver_t::impl_t {
     // two CTA-level TMA-pipeline kernels that handle two vectors per pass (CUOPT_B200_EVAL=tma; measured 3x slower at
     // configs[3], profiles/r1/launch_list_c4_bench.md)
     if (const char* e = std::getenv("CUOPT_B200_EVAL")) eval_tma = std::string(e) == "tma";
+    if (st.detect_infeasibility) {
+      if (sharded())
+        throw lp_error(error_type_t::ValidationError, "infeasibility_detection is not available in multi-GPU solves yet");
+      eval_tma = false;  // needs the four products of the element-wise evaluation path
+      part_infeas.resize(6 * (size_t)grid_m + 12 * (size_t)grid_n);
+    }
     if (st.per_constraint_residual) {  // the linf residuals are only implemented on the element-wise evaluation path
       eval_tma = false;
       part_max.resize(2 * (size_t)std::max(grid_m, grid_n) * 2);
@@ -963,6 +970,8 @@ struct pdlp_solver_t::impl_t {
     k.l2_norm_c                = l2_norm_c;
     k.reduced_cost_rule        = hp.handle_some_primal_gradients_on_finite_bounds_as_residuals ? 1 : 0;
     k.per_constraint_residual  = st.per_constraint_residual ? 1 : 0;
+    k.primal_infeasible_tol    = st.primal_infeasible_tolerance;
+    k.dual_infeasible_tol      = st.dual_infeasible_tolerance;
     return k;
   }
 
@@ -1029,6 +1038,16 @@ struct pdlp_solver_t::impl_t {
                                                               part_cols.data(), rows_src, rows_count, eval_consts(),
                                                               d_eval.data(), max_cols, max_rows, max_rows_count);
       launches += 3;
+      if (st.detect_infeasibility) {  // single GPU only (checked in build)
+        double* rows_parts = part_infeas.data();
+        double* cols_parts = part_infeas.data() + 6 * (size_t)grid_m;
+        k_infeasibility_rows<<<grid_m, EW_THREADS, 0, stream>>>(m, eval_m.data(), eval_m.data() + m, ybuf[cur].data(),
+                                                                y_avg.data(), lc.data(), uc.data(), rows_parts);
+        k_infeasibility_cols<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, aty2, aty2 + n, xbuf[cur].data(),
+                                                                x_avg.data(), c.data(), l.data(), u.data(), cols_parts,
+                                                                rows_parts, grid_m, eval_consts(), d_eval.data());
+        launches += 2;
+      }
     }
     launches += 4;
     check_launch();
@@ -1112,6 +1131,16 @@ struct pdlp_solver_t::impl_t {
     }
     if (sa == 1) { fill_solution(true, termination_status_t::Optimal); return true; }
     if (sc == 1) { fill_solution(false, termination_status_t::Optimal); return true; }
+    if (st.detect_infeasibility) {  // pdlp.cu:716-770: strict -> either iterate suffices, else both must agree
+      const bool ic = sc == 2 || sc == 3, ia = sa == 2 || sa == 3;
+      if (st.strict_infeasibility) {
+        if (ic) { fill_solution(false, static_cast<termination_status_t>(sc)); return true; }
+        if (ia) { fill_solution(true, static_cast<termination_status_t>(sa)); return true; }
+      } else if (ic && sc == sa) {
+        fill_solution(false, static_cast<termination_status_t>(sc));
+        return true;
+      }
+    }
     if (h_ctl->valid == -1) {  // :780-789
       fetch_ctl();
       sol                                        = lp_solution_t{};
