@@ -7,6 +7,7 @@
 #include "pdlp_solver.hpp"
 #include "solver_settings.hpp"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -392,6 +393,11 @@ cuopt_int_t cuOptSolve(cuOptOptimizationProblem problem, cuOptSolverSettings set
     if (run.method == 2 /* CUOPT_METHOD_DUAL_SIMPLEX */) {
       run.detect_infeasibility = true;
       run.strict_infeasibility = true;
+      // ... and a simplex answer is a vertex, accurate to ~1e-9 whatever the PDLP tolerances say (the reference's
+      // test_ranged_problem expects 32.0 +- 1e-3 from it; PDLP at the default 1e-4 stops at 31.9983)
+      for (double* t : {&run.absolute_dual_tolerance, &run.relative_dual_tolerance, &run.absolute_primal_tolerance,
+                        &run.relative_primal_tolerance, &run.absolute_gap_tolerance, &run.relative_gap_tolerance})
+        *t = std::min(*t, 1e-8);
     }
     h->sol = solve_lp(p, run);
     if (h->sol.error_status == 0) log_solution(ss.pdlp(), p, h->sol);
