@@ -44,6 +44,10 @@ def test_bad_parameter_name(ref):            # TEST(c_api, bad_parameter_name)
     assert ref.test_bad_parameter_name() == INVALID_ARGUMENT
 
 
+def test_burglar_is_a_mip_and_is_refused(ref):   # TEST(c_api, burglar) expects SUCCESS from the reference's MIP solver;
+    assert ref.burglar_problem() == VALIDATION_ERROR  # this LP-only build refuses before touching the GPU
+
+
 # ---- on the GPU ----------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_afiro(ref):                         # TEST(c_api, afiro): default method of solve_mps_file = DUAL_SIMPLEX
@@ -74,6 +78,3 @@ def test_ranged_problem(ref):                # TEST(c_api, test_ranged_problem)
     assert objective.value == pytest.approx(32.0, abs=1e-3)
 
 
-@pytest.mark.gpu
-def test_burglar_is_a_mip_and_is_refused(ref):   # TEST(c_api, burglar) expects SUCCESS from the reference's MIP solver
-    assert ref.burglar_problem() == VALIDATION_ERROR
