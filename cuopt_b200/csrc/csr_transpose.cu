@@ -135,6 +135,28 @@ void csr_split_columns_fill(int rows, const int* off, const int* idx, const doub
   CUOPT_CUDA_TRY(cudaStreamSynchronize(stream));
 }
 
+// ---- small CUB wrappers for the trust-region restart (trust_region.cuh): library calls once per major iteration ----
+// keys_out ascending (doubles >= 0 or +inf), vals_out = the permutation that sorts them (stable)
+void sort_keys_with_index(int count, const double* keys_in, double* keys_out, const int* vals_in, int* vals_out,
+                          cudaStream_t stream)
+{
+  size_t bytes = 0;
+  CUOPT_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, count, 0, 64, stream));
+  dvec<unsigned char> tmp(bytes + 16);
+  bytes = tmp.size();
+  CUOPT_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.data(), bytes, keys_in, keys_out, vals_in, vals_out, count, 0, 64, stream));
+  CUOPT_CUDA_TRY(cudaStreamSynchronize(stream));
+}
+void inclusive_sum_in_place(int count, double* values, cudaStream_t stream)
+{
+  size_t bytes = 0;
+  CUOPT_CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, bytes, values, values, count, stream));
+  dvec<unsigned char> tmp(bytes + 16);
+  bytes = tmp.size();
+  CUOPT_CUDA_TRY(cub::DeviceScan::InclusiveSum(tmp.data(), bytes, values, values, count, stream));
+  CUOPT_CUDA_TRY(cudaStreamSynchronize(stream));
+}
+
 // toff must hold cols + 1 ints, tidx / tval nnz elements.  All pointers are device pointers.
 void csr_transpose_device(int rows, int cols, int nnz, const int* off, const int* idx, const double* val, int* toff,
                           int* tidx, double* tval, cudaStream_t stream)

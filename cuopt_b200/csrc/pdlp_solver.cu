@@ -16,6 +16,7 @@
 
 #include "dist_comm.hpp"
 #include "pdlp_kernels.cuh"
+#include "trust_region.cuh"
 
 #include <math_constants.h>
 
@@ -179,6 +180,9 @@ void upload_csr(csr_dev_t& d, int rows, int cols, const std::vector<int>& off, c
 void csr_transpose_device(int rows, int cols, int nnz, const int* off, const int* idx, const double* val, int* toff,
                           int* tidx, double* tval, cudaStream_t stream);  // csr_transpose.cu
 
+void sort_keys_with_index(int count, const double* keys_in, double* keys_out, const int* vals_in, int* vals_out,
+                          cudaStream_t stream);  // csr_transpose.cu (CUB)
+void inclusive_sum_in_place(int count, double* values, cudaStream_t stream);
 void csr_split_columns_offsets(int rows, const int* off, const int* idx, int width, int n_blocks, int* const* blk_off,
                                int* blk_nnz_host, cudaStream_t stream);  // csr_transpose.cu
 void csr_split_columns_fill(int rows, const int* off, const int* idx, const double* val, int width, int n_blocks,
@@ -257,6 +261,16 @@ struct pdlp_solver_t::impl_t {
   dvec<double> eval_m, eval_n;  // A x (current, average) and, on one GPU, A^T y (current, average)
   dvec<double> part_max;        // per_constraint_residual: per-CTA maxima, rows (2 x grid_m) then columns (2 x grid_n)
   dvec<double> part_infeas;     // infeasibility detection: rows (6 x grid_m) then columns (12 x grid_n)
+  // trust-region restart (Methodical1), EXPERIMENTAL: trust_region.cuh
+  bool tr_enabled = false;
+  double tr_gap_reduction_last_trial = 1.0;  // never initialised in the reference (pdlp_restart_strategy.cu:160); 1 as in PDLP.jl
+  int grid_tr = 1;
+  dvec<double> tr_aty, tr_ax, tr_grad, tr_dir, tr_thr, tr_thr_sorted, tr_A, tr_B, tr_parts, tr_scal;
+  dvec<int> tr_iota, tr_perm;
+  struct tr_gap_t {
+    const double *px, *py;
+    double pd = 0, dd = 0, dist = 0, lower = 0, upper = 0, ngap = 0;
+  };
   // gather blocking (pdlp_kernels.cuh): the scaled A / A^T cut into column blocks whose slice of the gathered vector
   // is L2-sized; B == 1 (small LPs) keeps the fused kernels
   struct gather_blocks_t {
@@ -427,6 +441,20 @@ struct pdlp_solver_t::impl_t {
     // two CTA-level TMA-pipeline kernels that handle two vectors per pass (CUOPT_B200_EVAL=tma; measured 3x slower at
     // configs[3], profiles/r1/launch_list_c4_bench.md)
     if (const char* e = std::getenv("CUOPT_B200_EVAL")) eval_tma = std::string(e) == "tma";
+    if (hp.restart_strategy == 2) {
+      if (const char* e = std::getenv("CUOPT_B200_EXPERIMENTAL_METHODICAL1")) tr_enabled = e[0] == '1';
+      if (tr_enabled) {
+        if (sharded())
+          throw lp_error(error_type_t::ValidationError, "Methodical1 is not available in multi-GPU solves");
+        const size_t N = (size_t)n + m;
+        grid_tr        = ew_grid((int)std::min<size_t>(N, 1u << 30), sms);
+        tr_aty.resize(n); tr_ax.resize(m); tr_grad.resize(N); tr_dir.resize(N); tr_thr.resize(N); tr_thr_sorted.resize(N);
+        tr_A.resize(N); tr_B.resize(N); tr_iota.resize(N); tr_perm.resize(N);
+        tr_parts.resize(5 * (size_t)grid_tr);
+        tr_scal.resize(TR_SCALARS);
+        tr_scal.zero(stream);
+      }
+    }
     if (st.detect_infeasibility) {
       if (sharded())
         throw lp_error(error_type_t::ValidationError, "infeasibility_detection is not available in multi-GPU solves yet");
@@ -1154,6 +1182,105 @@ struct pdlp_solver_t::impl_t {
     return check_limits();
   }
 
+  // ---- trust-region restart (Methodical1), EXPERIMENTAL: mirrors oracle_t::run_trust_region_restart ----
+  double tr_weighted_distance(double pd, double dd) const  // pdlp_restart_strategy.cu:804-817
+  {
+    const double w = h_ctl->primal_weight;
+    return std::sqrt(pd * hp.primal_distance_smoothing * w + dd * (hp.dual_distance_smoothing / w));
+  }
+  void tr_distances(tr_gap_t& g)  // :1681-1714
+  {
+    k_restart_distance_and_weight<<<grid_misc, EW_THREADS, 0, stream>>>(d_ctl.data(), n, g.px, x_lr.data(), m, g.py,
+                                                                        y_lr.data(), hp.primal_weight_update_smoothing,
+                                                                        part_misc.data(), d_scalar.data());
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(h_scalar, d_scalar.data(), 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    sync();
+    g.pd   = h_scalar[0];
+    g.dd   = h_scalar[1];
+    g.dist = tr_weighted_distance(g.pd, g.dd);
+  }
+  void tr_bound(tr_gap_t& g)  // bound_optimal_objective, :1034-1051
+  {
+    const int N = n + m;
+    launch_spmv(ATs, g.py, tr_aty.data());
+    launch_spmv(As, g.px, tr_ax.data());
+    h_scalar[0] = g.dist;
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(tr_scal.data() + 5, h_scalar, sizeof(double), cudaMemcpyHostToDevice, stream));
+    tr_problem_t P{n, m, g.px, g.py, tr_aty.data(), tr_ax.data(), cs.data(), ls.data(), us.data(), lcs.data(), ucs.data()};
+    k_tr_prepare<<<grid_tr, EW_THREADS, 0, stream>>>(d_ctl.data(), P, tr_dir.data(), tr_thr.data(), tr_grad.data(),
+                                                     tr_iota.data(), tr_parts.data(), tr_scal.data());
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(h_scalar, tr_scal.data() + 3, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    sync();
+    const bool degenerate = g.dist == 0.0 || h_scalar[0] == 0.0;  // :1420-1431
+    if (!degenerate) {
+      sort_keys_with_index(N, tr_thr.data(), tr_thr_sorted.data(), tr_iota.data(), tr_perm.data(), stream);
+      k_tr_weights<<<grid_tr, EW_THREADS, 0, stream>>>(d_ctl.data(), n, N, tr_thr_sorted.data(), tr_perm.data(),
+                                                       tr_dir.data(), tr_A.data(), tr_B.data());
+      inclusive_sum_in_place(N, tr_A.data(), stream);
+      inclusive_sum_in_place(N, tr_B.data(), stream);
+      k_tr_bisect<<<1, 1, 0, stream>>>(N, tr_thr_sorted.data(), tr_A.data(), tr_B.data(), tr_scal.data());
+    }
+    k_tr_bounds<<<grid_tr, EW_THREADS, 0, stream>>>(d_ctl.data(), P, tr_dir.data(), tr_grad.data(), degenerate ? 1 : 0,
+                                                    tr_parts.data(), tr_scal.data());
+    check_launch();
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(h_scalar, tr_scal.data() + 7, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    sync();
+    g.lower = h_scalar[0];
+    g.upper = h_scalar[1];
+    launches += degenerate ? 4 : 6;
+  }
+  void trust_region_restart()  // pdlp_restart_strategy.cu:278-364
+  {
+    if (h_ctl->its_since_restart == 0) return;
+    const int cur = h_ctl->parity;
+    bool restart  = should_do_artificial_restart(total_pdlp_iterations);
+    tr_gap_t avg{x_avg.data(), y_avg.data()}, curg{xbuf[cur].data(), ybuf[cur].data()};
+    tr_distances(avg);
+    tr_distances(curg);
+    tr_bound(avg);
+    tr_bound(curg);
+    avg.ngap  = (avg.upper - avg.lower) / avg.dist;
+    curg.ngap = (curg.upper - curg.lower) / curg.dist;
+    const bool to_avg = curg.ngap / curg.dist >= avg.ngap / avg.dist;  // pick_restart_candidate :842-873
+    tr_gap_t& cand    = to_avg ? avg : curg;
+    if (!restart) {  // should_do_adaptive_restart_normalized_duality_gap :903-937
+      tr_gap_t last{x_lr.data(), y_lr.data()};
+      last.pd   = cand.pd;
+      last.dd   = cand.dd;
+      last.dist = tr_weighted_distance(cand.pd, cand.dd);
+      tr_bound(last);
+      last.ngap          = (last.upper - last.lower) / last.dist;
+      const double ratio = cand.ngap / last.ngap;
+      if (ratio < hp.necessary_reduction_for_restart &&
+          (ratio < hp.sufficient_reduction_for_restart || ratio > tr_gap_reduction_last_trial))
+        restart = true;
+      tr_gap_reduction_last_trial = ratio;
+    }
+    if (!restart) return;
+    const bool use_avg = to_avg && !hp.never_restart_to_average;
+    dvec<double>& cx   = to_avg ? x_avg : xbuf[cur];  // the candidate: new restart point and source of the weight update
+    dvec<double>& cy   = to_avg ? y_avg : ybuf[cur];
+    k_restart_distance_and_weight<<<grid_misc, EW_THREADS, 0, stream>>>(d_ctl.data(), n, cx.data(), x_lr.data(), m,
+                                                                        cy.data(), y_lr.data(),
+                                                                        hp.primal_weight_update_smoothing,
+                                                                        part_misc.data(), nullptr);
+    if (use_avg) {
+      xbuf[cur].copy_from(x_avg, stream);
+      ybuf[cur].copy_from(y_avg, stream);
+      need_aty = true;
+    }
+    last_restart_was_average = use_avg;
+    x_lr.copy_from(cx, stream);
+    y_lr.copy_from(cy, stream);
+    sum_x.zero(stream);
+    sum_y.zero(stream);
+    k_reset_after_restart<<<1, 1, 0, stream>>>(d_ctl.data());
+    launches += 2;
+    check_launch();
+    sol.stats.n_restarts += 1;
+    fetch_ctl();
+  }
+
   bool should_do_artificial_restart(int total_iterations) const  // pdlp_restart_strategy.cu:940-961
   {
     return h_ctl->its_since_restart >= hp.default_artificial_restart_threshold * total_iterations;
@@ -1245,9 +1372,12 @@ struct pdlp_solver_t::impl_t {
           launches += 4;
         }
         if (hp.restart_strategy == 1) kkt_restart();
-        else if (hp.restart_strategy == 2)
-          throw lp_error(error_type_t::ValidationError,
-                         "pdlp_solver_mode Methodical1 (trust-region restart) is not implemented in this build");
+        else if (hp.restart_strategy == 2) {
+          if (!tr_enabled)
+            throw lp_error(error_type_t::ValidationError,
+                           "pdlp_solver_mode Methodical1 (trust-region restart) is not implemented in this build");
+          trust_region_restart();  // EXPERIMENTAL (CUOPT_B200_EXPERIMENTAL_METHODICAL1=1), see trust_region.cuh
+        }
         if (!hp.rescale_for_restart) {  // pdlp.cu:1168-1175
           k_scale_back<<<grid_n, EW_THREADS, 0, stream>>>(n, xbuf[cur].data(), Dc.data());
           k_scale_back<<<grid_m, EW_THREADS, 0, stream>>>(m, ybuf[cur].data(), Dr.data());
