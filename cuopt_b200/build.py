@@ -13,7 +13,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libcuopt.so")
 
 CU_SOURCES = ["pdlp_solver.cu", "csr_transpose.cu"]
-CPP_SOURCES = ["c_api.cpp", "mps_reader.cpp", "solver_settings.cpp", "dist_comm.cpp"]
+CPP_SOURCES = ["c_api.cpp", "mps_reader.cpp", "solver_settings.cpp", "dist_comm.cpp", "file_writers.cpp"]
 
 
 def nvcc_path() -> str:

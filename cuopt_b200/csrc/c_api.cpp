@@ -15,6 +15,11 @@
 
 using namespace cuopt_b200;
 
+namespace cuopt_b200 {
+bool write_problem_as_mps(const lp_problem_t& p, const std::string& path);  // file_writers.cpp
+bool write_solution_file(const lp_problem_t& p, const lp_solution_t& s, const std::string& path);
+}  // namespace cuopt_b200
+
 namespace {
 
 struct solution_handle_t {
@@ -379,6 +384,10 @@ cuopt_int_t cuOptSolve(cuOptOptimizationProblem problem, cuOptSolverSettings set
   const solver_settings_t& ss = *static_cast<const solver_settings_t*>(settings);
   auto* h                     = new (std::nothrow) solution_handle_t();
   if (!h) return CUOPT_OUT_OF_MEMORY;
+  if (!ss.pdlp().user_problem_file.empty()) {  // solve.cu:586-589, before anything touches the GPU
+    if (!write_problem_as_mps(p, ss.pdlp().user_problem_file))
+      std::fprintf(stderr, "Could not open file %s for writing\n", ss.pdlp().user_problem_file.c_str());
+  }
   if (p.is_mip()) {
     // LP-only build: answer with an error solution instead of a MIP search
     h->is_mip            = false;
@@ -401,6 +410,10 @@ cuopt_int_t cuOptSolve(cuOptOptimizationProblem problem, cuOptSolverSettings set
     }
     h->sol = solve_lp(p, run);
     if (h->sol.error_status == 0) log_solution(ss.pdlp(), p, h->sol);
+    if (h->sol.error_status == 0 && !ss.pdlp().sol_file.empty()) {  // solve.cu:598-601
+      if (!write_solution_file(p, h->sol, ss.pdlp().sol_file))
+        std::fprintf(stderr, "Could not open file: %s for solution output\n", ss.pdlp().sol_file.c_str());
+    }
   }
   *solution_ptr = h;
   return h->sol.error_status;
