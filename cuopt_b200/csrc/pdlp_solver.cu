@@ -1115,6 +1115,78 @@ struct pdlp_solver_t::impl_t {
     finished                                  = true;
   }
 
+  // ---- save_best_primal_so_far (pdlp.cu:333-463): the best of {current, average} by primal quality at every major
+  // iteration that did not terminate, returned instead of the current iterate when a limit is hit (:265-331) ----
+  struct quality_t {
+    bool feasible    = false;
+    double residual  = std::numeric_limits<double>::infinity();
+    double objective = std::numeric_limits<double>::infinity();  // -inf when maximising
+  };
+  quality_t best_quality;
+  bool have_best = false;
+  dvec<double> best_x, best_y, best_rc;
+  eval_t best_eval{};
+  int best_accepted = 0, best_attempts = 0;
+  bool first_is_better(const quality_t& a, const quality_t& b) const  // get_best_quality(current = a, other = b) == a
+  {
+    if (a.feasible && !b.feasible) return true;
+    if (!a.feasible && b.feasible) return false;
+    if (a.feasible && b.feasible) {
+      const bool lower = a.objective < b.objective;
+      return (!maximize && lower) || (maximize && !lower);
+    }
+    return a.residual < b.residual;
+  }
+  void record_best_primal_so_far()
+  {
+    if (!have_best && maximize) best_quality.objective = -std::numeric_limits<double>::infinity();
+    const quality_t qc{h_eval[0].status == 7, h_eval[0].l2_primal_residual, h_eval[0].primal_objective};
+    const quality_t qa{h_eval[1].status == 7, h_eval[1].l2_primal_residual, h_eval[1].primal_objective};
+    const bool cur_wins   = first_is_better(qc, qa);
+    const quality_t& cand = cur_wins ? qc : qa;
+    if (!first_is_better(cand, best_quality)) return;
+    best_quality  = cand;
+    const int cur = h_ctl->parity;
+    best_x.copy_from(cur_wins ? xbuf[cur] : x_avg, stream);  // unscaled at this point, like fill_solution's sources
+    best_y.copy_from(cur_wins ? ybuf[cur] : y_avg, stream);
+    best_rc.copy_from(cur_wins ? rc_cur : rc_avg, stream);
+    best_eval     = h_eval[cur_wins ? 0 : 1];
+    best_accepted = h_ctl->accepted;  // the reference fills the returned solution at record time (:441-447)
+    best_attempts = h_ctl->attempts;
+    have_best     = true;
+  }
+  bool fill_best_solution(termination_status_t status)
+  {
+    if (!(st.save_best_primal_so_far && have_best)) return false;
+    sol.primal.resize(n);
+    sol.dual.resize(m);
+    sol.reduced_cost.resize(n);
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(sol.primal.data(), best_x.data(), (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(sol.dual.data(), best_y.data(), (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(sol.reduced_cost.data(), best_rc.data(), (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    fetch_ctl();
+    const eval_t& e                   = best_eval;
+    sol.termination_status            = status;
+    sol.error_status                  = 0;
+    lp_stats_t& s                     = sol.stats;
+    s.number_of_steps_taken           = best_accepted;
+    s.total_number_of_attempted_steps = best_attempts;
+    s.l2_primal_residual              = e.l2_primal_residual;
+    s.l2_dual_residual                = e.l2_dual_residual;
+    s.l2_relative_primal_residual     = e.l2_primal_residual / (1.0 + l2_norm_b);
+    s.l2_relative_dual_residual       = e.l2_dual_residual / (1.0 + l2_norm_c);
+    s.primal_objective                = e.primal_objective;
+    s.dual_objective                  = e.dual_objective;
+    s.gap                             = e.gap;
+    s.relative_gap                    = e.gap / (1.0 + std::fabs(e.primal_objective) + std::fabs(e.dual_objective));
+    s.solved_by_pdlp                  = 1;
+    s.final_step_size                 = h_ctl->step_size;
+    s.final_primal_weight             = h_ctl->primal_weight;
+    s.kernel_launches                 = launches;
+    finished                          = true;
+    return true;
+  }
+
   bool check_limits()  // pdlp.cu:265-331
   {
     bool out_of_time = now_seconds() - t_start >= st.time_limit;
@@ -1127,11 +1199,11 @@ struct pdlp_solver_t::impl_t {
       out_of_time = h_scalar[1] > 0.5;
     }
     if (out_of_time) {
-      fill_solution(false, termination_status_t::TimeLimit);
+      if (!fill_best_solution(termination_status_t::TimeLimit)) fill_solution(false, termination_status_t::TimeLimit);
       return true;
     }
     if (h_ctl->accepted >= st.iteration_limit) {
-      fill_solution(false, termination_status_t::IterationLimit);
+      if (!fill_best_solution(termination_status_t::IterationLimit)) fill_solution(false, termination_status_t::IterationLimit);
       return true;
     }
     return false;
@@ -1179,6 +1251,7 @@ struct pdlp_solver_t::impl_t {
       finished                                   = true;
       return true;
     }
+    if (st.save_best_primal_so_far) record_best_primal_so_far();  // pdlp.cu:790-796
     return check_limits();
   }
 

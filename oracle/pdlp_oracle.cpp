@@ -89,6 +89,7 @@ struct settings_t {
   int detect_infeasibility;     // infeasibility_information.cu, termination_strategy.cu:229-250, pdlp.cu:716-770
   int strict_infeasibility;
   double primal_infeasible_tol, dual_infeasible_tol;
+  int save_best_primal_so_far;  // pdlp.cu:333-463, :265-331
 };
 
 struct stats_t {
@@ -678,15 +679,62 @@ class oracle_t {
     result.solution_is_average             = is_avg ? 1 : 0;
   }
 
+  // save_best_primal_so_far (pdlp.cu:333-463): quality = primal feasible first, then objective; else least l2 residual
+  struct quality_t {
+    bool feasible    = false;
+    double residual  = INFINITY;
+    double objective = INFINITY;  // -inf when maximising (pdlp.cu ctor)
+  };
+  quality_t best_quality;
+  bool have_best = false;
+  stats_t best_result{};
+  std::vector<double> best_x, best_y, best_rc;
+  bool first_is_better(const quality_t& a, const quality_t& b) const  // get_best_quality(current = a, other = b) == a
+  {
+    if (a.feasible && !b.feasible) return true;
+    if (!a.feasible && b.feasible) return false;
+    if (a.feasible && b.feasible) {
+      const bool lower = a.objective < b.objective;
+      return (!maximize && lower) || (maximize && !lower);
+    }
+    return a.residual < b.residual;
+  }
+  void record_best_primal_so_far()
+  {
+    if (!have_best && best_quality.objective == INFINITY && maximize) best_quality.objective = -INFINITY;
+    const quality_t qc{conv_cur.status == 7, conv_cur.l2_primal_residual, conv_cur.primal_objective};
+    const quality_t qa{conv_avg.status == 7, conv_avg.l2_primal_residual, conv_avg.primal_objective};
+    const bool cur_wins      = first_is_better(qc, qa);
+    const quality_t& cand    = cur_wins ? qc : qa;
+    if (!first_is_better(cand, best_quality)) return;
+    best_quality = cand;
+    // fill_return_problem_solution at this moment (status is overwritten when a limit returns it)
+    const stats_t keep_r = result;
+    const auto keep_x = sol_x, keep_y = sol_y, keep_rc = sol_rc;
+    if (cur_wins) fill_solution(x, y, conv_cur, 5, false);
+    else fill_solution(x_avg, y_avg, conv_avg, 5, true);
+    best_result = result; best_x = sol_x; best_y = sol_y; best_rc = sol_rc;
+    result = keep_r; sol_x = keep_x; sol_y = keep_y; sol_rc = keep_rc;
+    have_best = true;
+  }
+  bool return_best(int status)
+  {
+    if (!(st.save_best_primal_so_far && have_best)) return false;
+    result = best_result;
+    result.termination_status = status;
+    sol_x = best_x; sol_y = best_y; sol_rc = best_rc;
+    return true;
+  }
+
   // pdlp.cu:265-331 (time limit is evaluated by the caller's clock)
   bool check_limits(double elapsed)
   {
     if (elapsed >= st.time_limit) {
-      fill_solution(x, y, conv_cur, 5, false);
+      if (!return_best(5)) fill_solution(x, y, conv_cur, 5, false);
       return true;
     }
     if (k_internal >= st.iteration_limit) {
-      fill_solution(x, y, conv_cur, 4, false);
+      if (!return_best(4)) fill_solution(x, y, conv_cur, 4, false);
       return true;
     }
     return false;
@@ -726,6 +774,7 @@ class oracle_t {
       sol_x.assign(n, 0.0); sol_y.assign(m, 0.0); sol_rc.assign(n, 0.0);
       return true;
     }
+    if (st.save_best_primal_so_far) record_best_primal_so_far();  // :790-796
     return check_limits(elapsed);
   }
 

@@ -56,6 +56,7 @@ class Settings(C.Structure):
         ("iteration_limit", C.c_int), ("time_limit", C.c_double), ("num_threads", C.c_int),
         ("per_constraint_residual", C.c_int), ("detect_infeasibility", C.c_int), ("strict_infeasibility", C.c_int),
         ("primal_infeasible_tol", C.c_double), ("dual_infeasible_tol", C.c_double),
+        ("save_best_primal_so_far", C.c_int),
     ]
 
 
@@ -172,7 +173,7 @@ class Oracle:
                  objective_offset=0.0, mode=STABLE2, hyper: Hyper | None = None, tol=1e-4, iteration_limit=2**31 - 1,
                  time_limit=float("inf"), tolerances: dict | None = None, per_constraint_residual=False,
                  num_threads: int = 0, detect_infeasibility=False, strict_infeasibility=False,
-                 primal_infeasible_tol=1e-8, dual_infeasible_tol=1e-8):
+                 primal_infeasible_tol=1e-8, dual_infeasible_tol=1e-8, save_best_primal_so_far=False):
         L = lib()
         self.m, self.n = len(con_lb), len(c)
         self._keep = [np.ascontiguousarray(offsets, np.int32), np.ascontiguousarray(indices, np.int32)] + [
@@ -187,6 +188,7 @@ class Oracle:
                                  strict_infeasibility=int(bool(strict_infeasibility)),
                                  primal_infeasible_tol=float(primal_infeasible_tol),
                                  dual_infeasible_tol=float(dual_infeasible_tol),
+                                 save_best_primal_so_far=int(bool(save_best_primal_so_far)),
                                  per_constraint_residual=int(bool(per_constraint_residual)), **t)
         k = self._keep
         self.h = C.c_void_p(L.pdlp_oracle_create(
