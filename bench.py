@@ -129,7 +129,9 @@ def workload(args):
     if args.workload == "c3":
         return lpgen.multicommodity(nodes=9000, arcs=27000, commodities=11, seed=1234)
     rows, cols = WORKLOADS[args.workload]
-    return lpgen.sparse_lp(args.rows or rows, args.cols or cols, args.nnz_per_row, seed=1234)
+    # --locality rho: fraction of each row's columns drawn from the row's own 1/8 column band (SURVEY §8d, C4's knob;
+    # 0 = uniform columns, the worst case for the gathers and the default)
+    return lpgen.sparse_lp(args.rows or rows, args.cols or cols, args.nnz_per_row, seed=1234, locality=args.locality)
 
 
 def config_dict(args, lp, n_gpus):
@@ -186,6 +188,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override the workload's row count (sparse_lp workloads)")
     ap.add_argument("--cols", type=int, default=0)
     ap.add_argument("--nnz-per-row", type=int, default=8)
+    ap.add_argument("--locality", type=float, default=0.0, help="column-locality knob rho of the sparse workloads")
     ap.add_argument("--iters", type=int, default=ITERS_PER_STEP)
     ap.add_argument("--cpu-iters", type=int, default=0,
                     help="oracle iterations per step (CPU arm / cpu_baseline); 0 = sized to ~20 s from the nnz count")
