@@ -1172,6 +1172,20 @@ void pdlp_oracle_set_warm_start(void* h, const double* const* vectors9, const do
   o->warm_given = true;
 }
 
+// Trust-region bounds at a caller-supplied point of the SCALED space (white-box test of the device reformulation):
+// out4 = {lower bound, upper bound, weighted distance used as radius, 0}; radius < 0 -> distance to the last restart.
+void pdlp_oracle_trust_region_bounds(void* h, const double* px, const double* py, double radius, double* out4)
+{
+  auto* o = static_cast<oracle_t*>(h);
+  oracle_t::local_gap_t g;
+  g.px.assign(px, px + o->n);
+  g.py.assign(py, py + o->m);
+  o->distance_from_last_restart(g);
+  if (radius >= 0.0) g.distance = radius;
+  o->bound_optimal_objective(g);
+  out4[0] = g.lower_bound; out4[1] = g.upper_bound; out4[2] = g.distance; out4[3] = 0.0;
+}
+
 // Named vectors / scalars for white-box comparisons.
 int pdlp_oracle_get_vector(void* h, const char* name, double* out)
 {

@@ -143,6 +143,7 @@ def lib():
         _lib.pdlp_oracle_trace.restype = C.c_int
         _lib.pdlp_oracle_single_attempt.argtypes = [C.c_void_p] + [C.c_void_p] * 3 + [C.c_double] * 2 + [C.c_void_p] * 5
         _lib.pdlp_oracle_convergence.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        _lib.pdlp_oracle_trust_region_bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         _lib.pdlp_oracle_get_warm_start.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.pdlp_oracle_set_warm_start.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
@@ -211,6 +212,13 @@ class Oracle:
         s = Stats()
         lib().pdlp_oracle_stats(self.h, C.byref(s))
         return s
+
+    def trust_region_bounds(self, px, py, radius: float = -1.0):
+        """(lower, upper, radius) of bound_optimal_objective at a point of the scaled space (Methodical1 restart)."""
+        px = np.ascontiguousarray(px, np.float64); py = np.ascontiguousarray(py, np.float64)
+        out = np.zeros(4)
+        lib().pdlp_oracle_trust_region_bounds(self.h, _p(px), _p(py), C.c_double(radius), _p(out))
+        return float(out[0]), float(out[1]), float(out[2])
 
     # ---- warm start (pdlp_warm_start_data.hpp:28-72): dict with the header's field names ----
     def get_warm_start(self) -> dict:
