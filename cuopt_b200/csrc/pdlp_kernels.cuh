@@ -11,13 +11,18 @@
 // x<->x' buffer swap all happen on the device (control block pdhg_ctl_t), so a
 // whole batch of attempts runs without the host.
 //
-// SpMV scheme ("row blocks"): the host cuts the CSR rows into consecutive blocks of
-// at most SPMV_NNZ nonzeros; a CTA streams a block's (col,val) entries with
-// coalesced evict-first loads, gathers the vector, parks the products in shared
-// memory (padded against bank conflicts) and then one thread per row adds that
-// row's products left to right and runs the fused row epilogue.  Matrix bytes are
-// read exactly once per pass; reductions use fixed-shape trees and a fixed grid,
-// so results are bit-reproducible run to run.
+// SpMV scheme ("warp blocks", spmv_warp.cuh): the host cuts the CSR rows into consecutive
+// blocks of at most 256 nonzeros and 32 rows (256 rows for very sparse matrices); ONE WARP
+// streams a block's (col,val) entries with coalesced evict-first loads, gathers the vector
+// (L1 no-allocate, L2 evict-last), parks the products in its own swizzled 2 KB of shared
+// memory and then one lane per row adds that row's products left to right and runs the
+// fused row epilogue; only __syncwarp, never __syncthreads.  Matrix bytes are read exactly
+// once per pass; reductions use fixed-shape trees and a fixed grid, so results are
+// bit-reproducible run to run.  For large LPs K2 / K3 are split by column blocks
+// ("gather blocking", further down); the sharded multi-GPU attempt and its NVLink peer
+// transport follow the single-GPU kernels; the evaluation / infeasibility kernels are
+// element-wise over products formed by k_spmv.  DESIGN.md §5 has the measurements behind
+// each of these choices.
 #pragma once
 
 #include "device_utils.cuh"
