@@ -36,7 +36,7 @@ class LPStats(C.Structure):
                 ("l2_dual_residual", C.c_double), ("l2_relative_dual_residual", C.c_double),
                 ("primal_objective", C.c_double), ("dual_objective", C.c_double), ("gap", C.c_double),
                 ("relative_gap", C.c_double), ("solved_by_pdlp", C.c_int32), ("n_major_iterations", C.c_int32),
-                ("n_restarts", C.c_int32), ("reserved", C.c_int32), ("solve_time", C.c_double),
+                ("n_restarts", C.c_int32), ("method_stand_in", C.c_int32), ("solve_time", C.c_double),
                 ("setup_seconds", C.c_double), ("pdhg_loop_seconds", C.c_double), ("termination_seconds", C.c_double),
                 ("initial_step_size", C.c_double), ("initial_primal_weight", C.c_double),
                 ("final_step_size", C.c_double), ("final_primal_weight", C.c_double), ("kernel_launches", C.c_int64)]

@@ -75,6 +75,11 @@ void log_solution(const pdlp_settings_t& st, const lp_problem_t& p, const lp_sol
   auto emit = [&](FILE* f) {
     std::fprintf(f, "Solving a problem with %d constraints %d variables (%d integers) and %d nonzeros\n", p.n_constraints,
                  p.n_variables, 0, p.nnz());
+    if (s.stats.method_stand_in == 1)
+      std::fprintf(f, "method Concurrent: this build has no CPU simplex to race, PDLP runs alone\n");
+    if (s.stats.method_stand_in == 2)
+      std::fprintf(f, "method DualSimplex: this build has no CPU simplex; PDLP stands in with strict infeasibility detection "
+                      "and tolerances tightened to <= 1e-8\n");
     std::fprintf(f, "   Iter    Primal Obj.      Dual Obj.    Gap        Primal Res.  Dual Res.   Time\n");
     std::fprintf(f, "%7d %+.8e %+.8e  %8.2e   %8.2e     %8.2e   %.3fs\n", s.stats.number_of_steps_taken,
                  s.stats.primal_objective, s.stats.dual_objective, s.stats.gap, s.stats.l2_primal_residual,
@@ -90,6 +95,23 @@ void log_solution(const pdlp_settings_t& st, const lp_problem_t& p, const lp_sol
       emit(f);
       std::fclose(f);
     }
+  }
+}
+
+// Maps anything thrown on the host side of a solve to an error solution: no C++ exception crosses the C boundary.
+template <typename F>
+void guarded(lp_solution_t& sol, F&& body)
+{
+  try {
+    body();
+  } catch (const std::bad_alloc&) {
+    sol                = lp_solution_t{};
+    sol.error_status   = CUOPT_OUT_OF_MEMORY;
+    sol.error_message  = "Memory allocation failed";
+  } catch (const std::exception& e) {
+    sol                = lp_solution_t{};
+    sol.error_status   = CUOPT_RUNTIME_ERROR;
+    sol.error_message  = e.what();
   }
 }
 
@@ -380,43 +402,54 @@ cuopt_int_t cuOptIsMIP(cuOptOptimizationProblem problem, cuopt_int_t* is_mip_ptr
 cuopt_int_t cuOptSolve(cuOptOptimizationProblem problem, cuOptSolverSettings settings, cuOptSolution* solution_ptr)
 {
   if (problem == nullptr || settings == nullptr || solution_ptr == nullptr) return CUOPT_INVALID_ARGUMENT;
+  *solution_ptr               = nullptr;
   const lp_problem_t& p       = *static_cast<const lp_problem_t*>(problem);
   const solver_settings_t& ss = *static_cast<const solver_settings_t*>(settings);
-  auto* h                     = new (std::nothrow) solution_handle_t();
+  std::unique_ptr<solution_handle_t> h(new (std::nothrow) solution_handle_t());
   if (!h) return CUOPT_OUT_OF_MEMORY;
-  if (!ss.pdlp().user_problem_file.empty()) {  // solve.cu:586-589, before anything touches the GPU
-    if (!write_problem_as_mps(p, ss.pdlp().user_problem_file))
-      std::fprintf(stderr, "Could not open file %s for writing\n", ss.pdlp().user_problem_file.c_str());
-  }
-  if (p.is_mip()) {
-    // LP-only build: answer with an error solution instead of a MIP search
-    h->is_mip            = false;
-    h->sol.error_status  = CUOPT_VALIDATION_ERROR;
-    h->sol.error_message = "cuopt-b200 implements the LP (PDLP) path only; the problem declares integer variables";
-  } else {
-    // method Concurrent / DualSimplex / PDLP all run PDLP here; crossover is not part of this build.  A caller who
-    // asks for the dual simplex explicitly gets what that method would tell apart — infeasible / unbounded LPs (the
-    // reference's test_infeasible_problem asks exactly that of CUOPT_METHOD_DUAL_SIMPLEX): PDLP stands in with its
-    // infeasibility detection switched on.  Concurrent (the default) keeps the caller's infeasibility_detection.
+  guarded(h->sol, [&]() {
+    if (!ss.pdlp().user_problem_file.empty()) {  // solve.cu:586-589, before anything touches the GPU
+      if (!write_problem_as_mps(p, ss.pdlp().user_problem_file))
+        std::fprintf(stderr, "Could not open file %s for writing\n", ss.pdlp().user_problem_file.c_str());
+    }
+    if (p.is_mip()) {
+      // LP-only build: answer with an error solution instead of a MIP search
+      h->is_mip            = false;
+      h->sol.error_status  = CUOPT_VALIDATION_ERROR;
+      h->sol.error_message = "cuopt-b200 implements the LP (PDLP) path only; the problem declares integer variables";
+      return;
+    }
+    // This build has no CPU simplex and no crossover.  What each `method` gets, and how the caller
+    // is told (log line below + cuOptB200LPStats.method_stand_in, INTEGRATION.md "method"):
+    //   PDLP        the requested method.
+    //   Concurrent  (the reference races PDLP against the dual simplex, solve.cu:467-536): PDLP alone, caller's settings.
+    //   DualSimplex PDLP stands in with what the simplex would tell apart or deliver: strict infeasibility detection (the
+    //               reference's test_infeasible_problem asks exactly that of CUOPT_METHOD_DUAL_SIMPLEX) and tolerances
+    //               tightened to 1e-8 where the caller's are looser (a simplex answer is a vertex, accurate to ~1e-9: the
+    //               reference's test_ranged_problem expects 32.0 +- 1e-3, PDLP at 1e-4 stops at 31.9983).  Tolerances the
+    //               caller already set below 1e-8, iteration_limit and time_limit are respected as given.
     pdlp_settings_t run = ss.pdlp();
+    int stand_in        = 0;
+    if (run.method == 0 /* CUOPT_METHOD_CONCURRENT */) stand_in = 1;
     if (run.method == 2 /* CUOPT_METHOD_DUAL_SIMPLEX */) {
+      stand_in                 = 2;
       run.detect_infeasibility = true;
       run.strict_infeasibility = true;
-      // ... and a simplex answer is a vertex, accurate to ~1e-9 whatever the PDLP tolerances say (the reference's
-      // test_ranged_problem expects 32.0 +- 1e-3 from it; PDLP at the default 1e-4 stops at 31.9983)
       for (double* t : {&run.absolute_dual_tolerance, &run.relative_dual_tolerance, &run.absolute_primal_tolerance,
                         &run.relative_primal_tolerance, &run.absolute_gap_tolerance, &run.relative_gap_tolerance})
         *t = std::min(*t, 1e-8);
     }
-    h->sol = solve_lp(p, run);
+    h->sol                       = solve_lp(p, run);
+    h->sol.stats.method_stand_in = stand_in;
     if (h->sol.error_status == 0) log_solution(ss.pdlp(), p, h->sol);
     if (h->sol.error_status == 0 && !ss.pdlp().sol_file.empty()) {  // solve.cu:598-601
       if (!write_solution_file(p, h->sol, ss.pdlp().sol_file))
         std::fprintf(stderr, "Could not open file: %s for solution output\n", ss.pdlp().sol_file.c_str());
     }
-  }
-  *solution_ptr = h;
-  return h->sol.error_status;
+  });
+  const cuopt_int_t status = h->sol.error_status;
+  *solution_ptr            = h.release();  // allocated even on failure: the error string stays retrievable (cuopt_c.cpp:611-618)
+  return status;
 }
 
 void cuOptDestroySolution(cuOptSolution* solution_ptr)
@@ -508,6 +541,7 @@ static void export_stats(const lp_stats_t& t, cuOptB200LPStats* o)
   o->solved_by_pdlp                  = t.solved_by_pdlp;
   o->n_major_iterations              = t.n_major_iterations;
   o->n_restarts                      = t.n_restarts;
+  o->method_stand_in                 = t.method_stand_in;
   o->solve_time                      = t.solve_time;
   o->setup_seconds                   = t.setup_seconds;
   o->pdhg_loop_seconds               = t.pdhg_loop_seconds;
@@ -767,18 +801,22 @@ cuopt_int_t cuOptB200SolveDistributed(cuOptOptimizationProblem local_rows_proble
     return CUOPT_INVALID_ARGUMENT;
   const lp_problem_t& p       = *static_cast<const lp_problem_t*>(local_rows_problem);
   const solver_settings_t& ss = *static_cast<const solver_settings_t*>(settings);
-  auto* h                     = new (std::nothrow) solution_handle_t();
+  *solution_ptr = nullptr;
+  std::unique_ptr<solution_handle_t> h(new (std::nothrow) solution_handle_t());
   if (!h) return CUOPT_OUT_OF_MEMORY;
-  if (p.is_mip()) {
-    h->sol.error_status  = CUOPT_VALIDATION_ERROR;
-    h->sol.error_message = "cuopt-b200 implements the LP (PDLP) path only; the problem declares integer variables";
-  } else {
+  guarded(h->sol, [&]() {
+    if (p.is_mip()) {
+      h->sol.error_status  = CUOPT_VALIDATION_ERROR;
+      h->sol.error_message = "cuopt-b200 implements the LP (PDLP) path only; the problem declares integer variables";
+      return;
+    }
     auto* d = static_cast<dist_context_t*>(dist);
     h->sol  = solve_lp(p, ss.pdlp(), d);
     if (h->sol.error_status == 0 && d->rank == 0) log_solution(ss.pdlp(), p, h->sol);
-  }
-  *solution_ptr = h;
-  return h->sol.error_status;
+  });
+  const cuopt_int_t status = h->sol.error_status;
+  *solution_ptr            = h.release();
+  return status;
 }
 
 cuopt_int_t cuOptB200ReadProblem(const char* filename, cuopt_int_t fixed_format, cuOptOptimizationProblem* problem_ptr)

@@ -13,6 +13,14 @@
 
 namespace cuopt_b200 {
 
+// SM count of the device the calling thread is bound to (a rank of a multi-GPU solve is not on device 0)
+static int current_device_sms()
+{
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
 namespace {
 
 __global__ void k_expand_rows_and_count(int rows, const int* __restrict__ off, const int* __restrict__ idx,
@@ -101,8 +109,7 @@ void csr_split_columns_offsets(int rows, const int* off, const int* idx, int wid
   if (n_blocks > MAX_COLUMN_BLOCKS) throw lp_error(error_type_t::RuntimeError, "too many column blocks");
   dvec<int> counts((size_t)n_blocks * (rows + 1));
   counts.zero(stream);
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int sms = current_device_sms();
   const int grid = std::max(1, std::min((rows + 255) / 256, sms * 8));
   k_block_count<<<grid, 256, 0, stream>>>(rows, off, idx, width, n_blocks, counts.data());
   CUOPT_CUDA_TRY(cudaGetLastError());
@@ -127,8 +134,7 @@ void csr_split_columns_fill(int rows, const int* off, const int* idx, const doub
     out.idx[b] = blk_idx[b];
     out.val[b] = blk_val[b];
   }
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int sms = current_device_sms();
   const int grid = std::max(1, std::min((rows + 255) / 256, sms * 8));
   k_block_fill<<<grid, 256, 0, stream>>>(rows, off, idx, val, width, out);
   CUOPT_CUDA_TRY(cudaGetLastError());
@@ -163,8 +169,7 @@ void csr_transpose_device(int rows, int cols, int nnz, const int* off, const int
 {
   dvec<int> entry_row(nnz), entry_id(nnz), keys_out(nnz), sorted_entry(nnz), col_count((size_t)cols + 1);
   col_count.zero(stream);
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int sms = current_device_sms();
   k_expand_rows_and_count<<<std::max(1, std::min((rows + 7) / 8, sms * 16)), 256, 0, stream>>>(
     rows, off, idx, entry_row.data(), entry_id.data(), col_count.data());
   CUOPT_CUDA_TRY(cudaGetLastError());

@@ -36,6 +36,7 @@ namespace cuopt_b200 {
 constexpr int EW_THREADS  = 256;  // element-wise kernels
 constexpr int PDHG_MIN_CTAS = 6;  // hot SpMV kernels: <= 40 registers, 6 x 256 threads per SM (measured optimum)
 constexpr int EVAL_STAGES = 3;    // two-vector evaluation kernels
+static __device__ int g_gather_ldg = 0;  // experiment: gathers as plain __ldg (CUOPT_B200_GATHER_LDG=1)
 static __device__ int g_l2_hints = 1;  // device_utils.cuh make_l2_policies; CUOPT_B200_L2_HINTS=0 clears it (measured: profiles/r1/l2_hints_experiment.txt)
 
 // Device-resident control block: every scalar the PDHG loop reads or writes.
@@ -104,6 +105,9 @@ __device__ __forceinline__ double gather_partials(const double* parts, int count
   for (int i = threadIdx.x; i < count; i += blockDim.x) s += __ldcg(parts + i);
   return block_reduce(s, red);
 }
+
+// gather policy of the SpMV kernels: evict-last hint (default) or 0 = plain __ldg (experiment switch g_gather_ldg)
+__device__ __forceinline__ unsigned long long gather_policy(const l2_policy_t& pol) { return g_gather_ldg ? 0ull : pol.keep; }
 
 // Adaptive step-size rule with accept / reject, executed by ONE thread per attempt
 // (adaptive_step_size_strategy.cu:92-188) plus the bookkeeping the reference does on the host in take_step
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_dual_step(const
     const double d   = next - p.y;
     dy2 += d * d;
   };
-  spmv_warp_rows<payload_t>(A, xbar, prod[threadIdx.x >> 5], pre_op, row_op, pol.keep);
+  spmv_warp_rows<payload_t>(A, xbar, prod[threadIdx.x >> 5], pre_op, row_op, gather_policy(pol));
   const double tot = block_reduce(dy2, red);
   if (threadIdx.x == 0) part_dy2[blockIdx.x] = tot;
 }
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_step(
     acc[0] += p.dx * (s - p.aty);
     acc[1] += p.dx * p.dx;
   };
-  spmv_warp_rows<payload_t>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op, pol.keep);
+  spmv_warp_rows<payload_t>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op, gather_policy(pol));
 
   if (!publish_and_elect<2>(acc, parts, &ctl->ticket[0], red)) return;
   const double interaction = gather_partials(parts, gridDim.x, red);
@@ -583,6 +587,41 @@ __global__ void k_step_rule_gather(pdhg_ctl_t* __restrict__ ctl, const double* _
 }
 
 // ---------------------------------------------------------------------------------------------
+// L2 warm-up of the vector an SpMV is about to gather from.  A gather that misses L2 costs the DRAM a row activation for
+// one 32-byte sector; the same bytes read sequentially cost ~1/20 of that (pages stay open).  The vector (or the column
+// block's slice of it) is therefore pulled into L2 by a sequential sweep right before the gathers start: +8 bytes per
+// vector element of DRAM reads, in exchange for gathers that hit.  mode 1: 16-byte loads (evict-last), mode 2:
+// prefetch.global.L2::evict_last per 128-byte line.
+//   pick_candidate as in k_block_pass: 0 -> x0, 1 -> the candidate dual y' = parity ? x0 : x1
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) k_l2_warm(const pdhg_ctl_t* __restrict__ ctl,
+                                                        const double* __restrict__ x0,
+                                                        const double* __restrict__ x1,
+                                                        int pick_candidate,
+                                                        size_t first,
+                                                        size_t count,
+                                                        int mode)
+{
+  if (ctl != nullptr && !ctl->active) return;
+  const double* x = (pick_candidate ? (ctl->parity ? x0 : x1) : x0) + first;
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  if (mode == 2) {
+    for (size_t i = tid * 16; i < count; i += nthr * 16)
+      asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(x + i));
+    return;
+  }
+  unsigned long long keep;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+  const size_t head = ((16 - ((size_t)x & 15)) & 15) / 8;  // doubles before the first 16-byte boundary
+  double a, b, acc = 0.0;
+  for (size_t i = head + tid * 2; i + 1 < count; i += nthr * 2) {
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(a), "=d"(b) : "l"(x + i), "l"(keep));
+    acc += a + b;
+  }
+  if (acc == 1.2345e-300) asm volatile("trap;");  // keeps the loads alive
+}
+
+// ---------------------------------------------------------------------------------------------
 // Gather blocking (large LPs).  When the vector an SpMV gathers from is much larger than what stays in L2 (80 MB at
 // configs[3] against a 126 MB L2 that also sees ~2 GB of streams per kernel), ncu shows the fused kernels DRAM-bound
 // at 2.4x their algorithmic bytes: every gathered double drags a 32-byte sector in from HBM (profiles/r1).  The
@@ -619,7 +658,7 @@ __global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? PDHG_MIN_CTAS : 4) k_
     return p;
   };
   auto row_op = [&](int r, double s, const payload_t&) { st_l2(t + r, s, pol.stream); };
-  spmv_warp_rows<payload_t, RPL, true>(Ab, x, prod[threadIdx.x >> 5], pre_op, row_op, pol.keep);
+  spmv_warp_rows<payload_t, RPL, true>(Ab, x, prod[threadIdx.x >> 5], pre_op, row_op, gather_policy(pol));
 }
 
 // K2 epilogue on t = A * xbar (the row_op of k_dual_step, element-wise).
@@ -740,10 +779,13 @@ __global__ void __launch_bounds__(EW_THREADS) k_flush_average(const pdhg_ctl_t* 
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) sum_y[i] = sum_y[i] + w * y[i];
 }
 __global__ void k_clear_pending(pdhg_ctl_t* ctl) { ctl->pending_avg = 0; }
+// take_step starts from set_valid_step_size(0) (pdlp.cu:1191): a batch that follows a zero-movement step tries again, so
+// the iteration count keeps advancing and the next termination test can answer Optimal / NumericalError (pdlp.cu:780-789)
 __global__ void k_begin_batch(pdhg_ctl_t* ctl, int steps)
 {
   ctl->target = ctl->accepted + steps;
-  ctl->active = (steps > 0 && ctl->valid != -1) ? 1 : 0;
+  ctl->valid  = 0;
+  ctl->active = steps > 0 ? 1 : 0;
 }
 
 // Plain y = A x on the row-block scheme (A^T y after a restart to the average, pdhg.cu:120-134).

@@ -261,7 +261,7 @@ struct pdlp_solver_t::impl_t {
   dvec<double> eval_m, eval_n;  // A x (current, average) and, on one GPU, A^T y (current, average)
   dvec<double> part_max;        // per_constraint_residual: per-CTA maxima, rows (2 x grid_m) then columns (2 x grid_n)
   dvec<double> part_infeas;     // infeasibility detection: rows (6 x grid_m) then columns (12 x grid_n)
-  // trust-region restart (Methodical1), EXPERIMENTAL: trust_region.cuh
+  // trust-region restart (Methodical1): trust_region.cuh
   bool tr_enabled = false;
   double tr_gap_reduction_last_trial = 1.0;  // never initialised in the reference (pdlp_restart_strategy.cu:160); 1 as in PDLP.jl
   int grid_tr = 1;
@@ -281,6 +281,7 @@ struct pdlp_solver_t::impl_t {
   };
   gather_blocks_t blkA, blkAT;
   dvec<double> t_m, t_n;
+  int l2_warm = 0;  // 0 off, 1 sequential loads, 2 prefetch instructions (k_l2_warm); CUOPT_B200_L2_WARM
   size_t gather_block_bytes = 40u << 20;  // measured optimum at configs[3] (profiles/r1/gather_block_sweep_c4.txt)
   int n_part_dy2 = 1;  // CTAs that publish ||dy||^2 partials: grid_k2 (fused K2) or grid_m (blocked K2 epilogue)
   int grid_k1 = 1, grid_k2 = 1, grid_k3 = 1, grid_er = 1, grid_ec = 1, grid_n = 1, grid_m = 1, grid_misc = 1;
@@ -435,6 +436,12 @@ struct pdlp_solver_t::impl_t {
     n_part_dy2 = grid_k2;
     // size of the slice of the gathered vector one column block may span (0 = never block); bytes, for the tests too
     if (const char* e = std::getenv("CUOPT_B200_GATHER_BLOCK_BYTES")) gather_block_bytes = (size_t)std::atoll(e);
+    if (const char* e = std::getenv("CUOPT_B200_L2_WARM")) l2_warm = std::atoi(e);
+    {
+      const char* e = std::getenv("CUOPT_B200_GATHER_LDG");
+      const int on  = (e != nullptr && e[0] == '1') ? 1 : 0;
+      CUOPT_CUDA_TRY(cudaMemcpyToSymbol(g_gather_ldg, &on, sizeof(int)));
+    }
     part_k3.resize(2 * (size_t)std::max(grid_k3, grid_n));
     part_rows.resize(6 * (size_t)std::max(grid_er, grid_m));
     // evaluation of the iterates: four SpMVs on the warp-block core + element-wise row / column math (default), or the
@@ -442,8 +449,8 @@ struct pdlp_solver_t::impl_t {
     // configs[3], profiles/r1/launch_list_c4_bench.md)
     if (const char* e = std::getenv("CUOPT_B200_EVAL")) eval_tma = std::string(e) == "tma";
     if (hp.restart_strategy == 2) {
-      if (const char* e = std::getenv("CUOPT_B200_EXPERIMENTAL_METHODICAL1")) tr_enabled = e[0] == '1';
-      if (tr_enabled) {
+      tr_enabled = true;
+      {
         if (sharded())
           throw lp_error(error_type_t::ValidationError, "Methodical1 is not available in multi-GPU solves");
         const size_t N = (size_t)n + m;
@@ -770,12 +777,24 @@ struct pdlp_solver_t::impl_t {
     t.resize((size_t)M.rows);
     t.zero(stream);
   }
+  // sequential sweep that pulls [first, first + count) of the vector the next SpMV gathers from into L2 (k_l2_warm)
+  void launch_l2_warm(const double* x0, const double* x1, int pick_candidate, size_t first, size_t count)
+  {
+    if (!l2_warm || count == 0) return;
+    const size_t per_thread = l2_warm == 2 ? 16 : 2;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((count / per_thread + EW_THREADS - 1) / EW_THREADS, (size_t)sms * 8));
+    k_l2_warm<<<grid, EW_THREADS, 0, stream>>>(d_ctl.data(), x0, x1, pick_candidate, first, count, l2_warm);
+  }
   // t (+)= M_b * x for every column block, in block order
   void launch_block_passes(const gather_blocks_t& g, const double* x0, const double* x1, int pick_candidate, double* t,
                            const unsigned long long* wait_flags, int n_wait)
   {
     for (int b = 0; b < g.B; ++b) {
       const csr_dev_t& M = g.blk[b];
+      if (wait_flags == nullptr) {
+        const size_t first = (size_t)b * g.width;
+        launch_l2_warm(x0, x1, pick_candidate, first, std::min<size_t>(g.width, (size_t)M.cols - first));
+      }
       const unsigned long long* wf = b == 0 ? wait_flags : nullptr;
       if (M.wide())
         k_block_pass<WARP_WIDE_RPL><<<g.grid[b], WARP_THREADS, 0, stream>>>(d_ctl.data(), M.warp_view_wide(), x0, x1,
@@ -789,6 +808,7 @@ struct pdlp_solver_t::impl_t {
   void enqueue_k2(const unsigned long long* wait_flags, int n_wait)
   {
     if (!blkA.on()) {
+      if (wait_flags == nullptr) launch_l2_warm(xbar.data(), xbar.data(), 0, 0, (size_t)n);
       k_dual_step<<<grid_k2, WARP_THREADS, 0, stream>>>(d_ctl.data(), As.warp_view(), xbar.data(), ybuf[0].data(),
                                                         ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(), part_dy2.data(),
                                                         wait_flags, n_wait);
@@ -802,6 +822,7 @@ struct pdlp_solver_t::impl_t {
   void enqueue_k3()
   {
     if (!blkAT.on()) {
+      launch_l2_warm(ybuf[0].data(), ybuf[1].data(), 1, 0, (size_t)m);
       k_transpose_step<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
                                                              xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
                                                              atybuf[1].data(), part_k3.data(), part_dy2.data(), n_part_dy2);
@@ -1183,6 +1204,7 @@ struct pdlp_solver_t::impl_t {
     s.final_step_size                 = h_ctl->step_size;
     s.final_primal_weight             = h_ctl->primal_weight;
     s.kernel_launches                 = launches;
+    if (st.capture_warm_start) capture_warm_start();  // continuing after a limit is the main use of a warm start
     finished                          = true;
     return true;
   }
@@ -1243,7 +1265,9 @@ struct pdlp_solver_t::impl_t {
     }
     if (h_ctl->valid == -1) {  // :780-789
       fetch_ctl();
+      const lp_stats_t kept                      = sol.stats;  // setup / loop times, restarts, major iterations so far
       sol                                        = lp_solution_t{};
+      sol.stats                                  = kept;
       sol.termination_status                     = termination_status_t::NumericalError;
       sol.stats.number_of_steps_taken            = h_ctl->accepted;
       sol.stats.total_number_of_attempted_steps  = h_ctl->attempts;
@@ -1255,7 +1279,7 @@ struct pdlp_solver_t::impl_t {
     return check_limits();
   }
 
-  // ---- trust-region restart (Methodical1), EXPERIMENTAL: mirrors oracle_t::run_trust_region_restart ----
+  // ---- trust-region restart (Methodical1): mirrors oracle_t::run_trust_region_restart ----
   double tr_weighted_distance(double pd, double dd) const  // pdlp_restart_strategy.cu:804-817
   {
     const double w = h_ctl->primal_weight;
@@ -1446,10 +1470,7 @@ struct pdlp_solver_t::impl_t {
         }
         if (hp.restart_strategy == 1) kkt_restart();
         else if (hp.restart_strategy == 2) {
-          if (!tr_enabled)
-            throw lp_error(error_type_t::ValidationError,
-                           "pdlp_solver_mode Methodical1 (trust-region restart) is not implemented in this build");
-          trust_region_restart();  // EXPERIMENTAL (CUOPT_B200_EXPERIMENTAL_METHODICAL1=1), see trust_region.cuh
+          trust_region_restart();  // trust_region.cuh
         }
         if (!hp.rescale_for_restart) {  // pdlp.cu:1168-1175
           k_scale_back<<<grid_n, EW_THREADS, 0, stream>>>(n, xbuf[cur].data(), Dc.data());

@@ -201,6 +201,7 @@ struct lp_stats_t {
   double gap                          = 0;
   double relative_gap                 = 0;
   int solved_by_pdlp                  = 1;
+  int method_stand_in                 = 0;  // 0: the requested method ran; 1: Concurrent -> PDLP alone; 2: DualSimplex -> PDLP stand-in (c_api.cpp)
   double solve_time                   = 0;  // seconds, wall clock of run_solver (reference semantics)
   // --- this build ---
   double setup_seconds       = 0;  // H2D upload + transpose + scaling

@@ -1,7 +1,6 @@
-// Trust-region restart of the Methodical1 preset on the device — EXPERIMENTAL in round 1: written against the oracle
-// restatement (oracle/pdlp_oracle.cpp: run_trust_region_restart / bound_optimal_objective, pinned to the reference's
-// test_very_low_tolerance) but not yet run on a GPU; it is reachable only with CUOPT_B200_EXPERIMENTAL_METHODICAL1=1,
-// otherwise pdlp_solver_mode = 2 keeps answering CUOPT_VALIDATION_ERROR.
+// Trust-region restart of the Methodical1 preset on the device, written against the oracle restatement
+// (oracle/pdlp_oracle.cpp: run_trust_region_restart / bound_optimal_objective, pinned to the reference's
+// test_very_low_tolerance).  GPU acceptance: tests/test_methodical1.py (first run and green in round 2).
 //
 // Reference: restart_strategy/pdlp_restart_strategy.cu:278-364 (flow), :1034-1078 (bound_optimal_objective,
 // compute_bound), :1291-1678 (trust-region solve), :1717-1900 (gradients, Lagrangian), utils.cuh:240-345.

