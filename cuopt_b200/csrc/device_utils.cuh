@@ -139,10 +139,8 @@ __device__ __forceinline__ l2_policy_t make_l2_policies(int mode)
   }
   return p;
 }
-// policy == 0: plain read-only load (L1 allocation, L2 evict-normal)
 __device__ __forceinline__ double ld_l2(const double* p, unsigned long long policy)
 {
-  if (policy == 0ull) return __ldg(p);
   double v;
   asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
   return v;

@@ -11,32 +11,25 @@
 // x<->x' buffer swap all happen on the device (control block pdhg_ctl_t), so a
 // whole batch of attempts runs without the host.
 //
-// SpMV scheme ("warp blocks", spmv_warp.cuh): the host cuts the CSR rows into consecutive
-// blocks of at most 256 nonzeros and 32 rows (256 rows for very sparse matrices); ONE WARP
-// streams a block's (col,val) entries with coalesced evict-first loads, gathers the vector
-// (L1 no-allocate, L2 evict-last), parks the products in its own swizzled 2 KB of shared
-// memory and then one lane per row adds that row's products left to right and runs the
-// fused row epilogue; only __syncwarp, never __syncthreads.  Matrix bytes are read exactly
-// once per pass; reductions use fixed-shape trees and a fixed grid, so results are
-// bit-reproducible run to run.  For large LPs K2 / K3 are split by column blocks
-// ("gather blocking", further down); the sharded multi-GPU attempt and its NVLink peer
-// transport follow the single-GPU kernels; the evaluation / infeasibility kernels are
-// element-wise over products formed by k_spmv.  DESIGN.md §5 has the measurements behind
-// each of these choices.
+// SpMV scheme (spmv_bicsr.cuh): every matrix lives in block-interleaved CSR — blocks of whole rows with at most 256
+// entries, stored so that one coalesced load hands each lane 8 CONSECUTIVE entries; ONE WARP streams a block (evict-first),
+// gathers the vector (L1 no-allocate, L2 evict-last), adds its products in registers (left to right per lane, carries between
+// lanes by shuffle) and passes one double per row through shared memory to the lane that runs the fused row epilogue; only
+// __syncwarp, never __syncthreads.  Matrix bytes are read exactly once per pass; reductions use fixed-shape trees and a
+// fixed grid, so results are bit-reproducible run to run.  For large LPs K2 / K3 are split by column blocks ("gather
+// blocking", further down) with the row epilogue fused into the LAST block's pass; the sharded multi-GPU attempt and its
+// NVLink peer transport follow the single-GPU kernels; the evaluation / infeasibility kernels are element-wise over
+// products formed by k_spmv.  DESIGN.md §5 has the measurements behind each of these choices.
 #pragma once
 
 #include "device_utils.cuh"
-#include "spmv_pipeline.cuh"
-#include "spmv_warp.cuh"
+#include "spmv_bicsr.cuh"
 
 #include <math_constants.h>
 
 namespace cuopt_b200 {
 
 constexpr int EW_THREADS  = 256;  // element-wise kernels
-constexpr int PDHG_MIN_CTAS = 6;  // hot SpMV kernels: <= 40 registers, 6 x 256 threads per SM (measured optimum)
-constexpr int EVAL_STAGES = 3;    // two-vector evaluation kernels
-static __device__ int g_gather_ldg = 0;  // experiment: gathers as plain __ldg (CUOPT_B200_GATHER_LDG=1)
 static __device__ int g_l2_hints = 1;  // device_utils.cuh make_l2_policies; CUOPT_B200_L2_HINTS=0 clears it (measured: profiles/r1/l2_hints_experiment.txt)
 
 // Device-resident control block: every scalar the PDHG loop reads or writes.
@@ -105,9 +98,6 @@ __device__ __forceinline__ double gather_partials(const double* parts, int count
   for (int i = threadIdx.x; i < count; i += blockDim.x) s += __ldcg(parts + i);
   return block_reduce(s, red);
 }
-
-// gather policy of the SpMV kernels: evict-last hint (default) or 0 = plain __ldg (experiment switch g_gather_ldg)
-__device__ __forceinline__ unsigned long long gather_policy(const l2_policy_t& pol) { return g_gather_ldg ? 0ull : pol.keep; }
 
 // Adaptive step-size rule with accept / reject, executed by ONE thread per attempt
 // (adaptive_step_size_strategy.cu:92-188) plus the bookkeeping the reference does on the host in take_step
@@ -249,20 +239,23 @@ __global__ void __launch_bounds__(EW_THREADS) k_primal_step(const pdhg_ctl_t* __
 // K2 — A*xbar and dual step.  y' = max(ybar + sigma lc, min(ybar + sigma uc, 0)), ybar = y - sigma (A xbar)
 // (pdhg.cu:73-117 + utils.cuh:98-112) + dual half of the running average + partial ||dy||^2.
 // =============================================================================================
-__global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_dual_step(const pdhg_ctl_t* __restrict__ ctl,
-                                                                           csr_warp_view_t A,
-                                                                           const double* __restrict__ xbar,
-                                                                           double* __restrict__ ybuf0,
-                                                                           double* __restrict__ ybuf1,
-                                                                           const double* __restrict__ lc,
-                                                                           const double* __restrict__ uc,
-                                                                           double* __restrict__ sum_y,
-                                                                           double* __restrict__ part_dy2,
-                                                                           const unsigned long long* xbar_flags,
-                                                                           int n_xbar_flags)
+// INIT: the product continues the running sum t of the earlier column blocks (gather blocking: this is the LAST block's pass)
+template <bool INIT>
+__global__ void __launch_bounds__(BICSR_THREADS, BICSR_MIN_CTAS) k_dual_step(const pdhg_ctl_t* __restrict__ ctl,
+                                                                             bicsr_view_t A,
+                                                                             const double* __restrict__ xbar,
+                                                                             double* __restrict__ ybuf0,
+                                                                             double* __restrict__ ybuf1,
+                                                                             const double* __restrict__ lc,
+                                                                             const double* __restrict__ uc,
+                                                                             double* __restrict__ sum_y,
+                                                                             double* __restrict__ part_dy2,
+                                                                             const unsigned long long* xbar_flags,
+                                                                             int n_xbar_flags,
+                                                                             const double* __restrict__ t)
 {
   if (!ctl->active) return;
-  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
+  __shared__ double rows[BICSR_WARPS][BICSR_SLOTS];
   __shared__ double red[32];
   // multi-GPU peer transport: xbar slices arrive by NVLink stores of the other ranks' K1s (see k_primal_step_bcast)
   if (xbar_flags) peer_wait(xbar_flags, n_xbar_flags, (unsigned long long)ctl->attempts + 1ull);
@@ -275,14 +268,15 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_dual_step(const
   double dy2         = 0.0;
   const l2_policy_t pol = make_l2_policies(g_l2_hints);
   struct payload_t {
-    double y, lc, uc, sum;
+    double y, lc, uc, sum, init;
   };
   auto pre_op = [&](int i) {
     payload_t p;
-    p.y   = y[i];
-    p.lc  = ld_stream(lc + i);
-    p.uc  = ld_stream(uc + i);
-    p.sum = pending ? sum_y[i] : 0.0;
+    p.y    = y[i];
+    p.lc   = ld_stream(lc + i);
+    p.uc   = ld_stream(uc + i);
+    p.sum  = pending ? sum_y[i] : 0.0;
+    p.init = INIT ? ld_l2(t + i, pol.stream) : 0.0;
     return p;
   };
   auto row_op = [&](int i, double s, const payload_t& p) {
@@ -295,7 +289,7 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_dual_step(const
     const double d   = next - p.y;
     dy2 += d * d;
   };
-  spmv_warp_rows<payload_t>(A, xbar, prod[threadIdx.x >> 5], pre_op, row_op, gather_policy(pol));
+  spmv_bicsr_rows<payload_t, INIT>(A, xbar, rows[threadIdx.x >> 5], pre_op, row_op, pol.keep);
   const double tot = block_reduce(dy2, red);
   if (threadIdx.x == 0) part_dy2[blockIdx.x] = tot;
 }
@@ -305,20 +299,23 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_dual_step(const
 // adaptive step-size rule with accept/reject (adaptive_step_size_strategy.cu:92-188, 232-345).
 // interaction = dx . (A^T y' - A^T y)  (the reference's SpMV-saving form, :267-277).
 // =============================================================================================
-__global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_step(pdhg_ctl_t* __restrict__ ctl,
-                                                                                csr_warp_view_t AT,
-                                                                                const double* __restrict__ ybuf0,
-                                                                                const double* __restrict__ ybuf1,
-                                                                                const double* __restrict__ xbuf0,
-                                                                                const double* __restrict__ xbuf1,
-                                                                                double* __restrict__ aty0,
-                                                                                double* __restrict__ aty1,
-                                                                                double* __restrict__ parts,  // 2 x gridDim.x
-                                                                                const double* __restrict__ part_dy2,
-                                                                                int n_part_dy2)
+// INIT: as in k_dual_step (the last column block's pass of a gather-blocked A^T y')
+template <bool INIT>
+__global__ void __launch_bounds__(BICSR_THREADS, BICSR_MIN_CTAS) k_transpose_step(pdhg_ctl_t* __restrict__ ctl,
+                                                                                  bicsr_view_t AT,
+                                                                                  const double* __restrict__ ybuf0,
+                                                                                  const double* __restrict__ ybuf1,
+                                                                                  const double* __restrict__ xbuf0,
+                                                                                  const double* __restrict__ xbuf1,
+                                                                                  double* __restrict__ aty0,
+                                                                                  double* __restrict__ aty1,
+                                                                                  double* __restrict__ parts,  // 2 x gridDim.x
+                                                                                  const double* __restrict__ part_dy2,
+                                                                                  int n_part_dy2,
+                                                                                  const double* __restrict__ t)
 {
   if (!ctl->active) return;
-  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
+  __shared__ double rows[BICSR_WARPS][BICSR_SLOTS];
   __shared__ double red[32];
   const int cur     = ctl->parity;
   const double* yn  = cur ? ybuf0 : ybuf1;  // candidate y'
@@ -329,12 +326,13 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_step(
   double acc[2]     = {0.0, 0.0};  // interaction, ||dx||^2
   const l2_policy_t pol = make_l2_policies(g_l2_hints);
   struct payload_t {
-    double dx, aty;
+    double dx, aty, init;
   };
   auto pre_op = [&](int j) {
     payload_t p;
-    p.dx  = ld_l2(xn + j, pol.stream) - ld_l2(x + j, pol.stream);
-    p.aty = ld_l2(aty + j, pol.stream);
+    p.dx   = ld_l2(xn + j, pol.stream) - ld_l2(x + j, pol.stream);
+    p.aty  = ld_l2(aty + j, pol.stream);
+    p.init = INIT ? ld_l2(t + j, pol.stream) : 0.0;
     return p;
   };
   auto row_op = [&](int j, double s, const payload_t& p) {
@@ -342,7 +340,7 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_step(
     acc[0] += p.dx * (s - p.aty);
     acc[1] += p.dx * p.dx;
   };
-  spmv_warp_rows<payload_t>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op, gather_policy(pol));
+  spmv_bicsr_rows<payload_t, INIT>(AT, yn, rows[threadIdx.x >> 5], pre_op, row_op, pol.keep);
 
   if (!publish_and_elect<2>(acc, parts, &ctl->ticket[0], red)) return;
   const double interaction = gather_partials(parts, gridDim.x, red);
@@ -358,20 +356,19 @@ __global__ void __launch_bounds__(WARP_THREADS, PDHG_MIN_CTAS) k_transpose_step(
 // A^T y' that is summed over ranks (NCCL all-reduce on the solver stream) between K3a and K3b.  The extra slot
 // buf[n] carries this rank's ||dy||^2 through the same collective.
 // ---------------------------------------------------------------------------------------------
-template <int RPL>
-__global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? PDHG_MIN_CTAS : 4) k_transpose_partial(const pdhg_ctl_t* __restrict__ ctl,
-                                                                                   csr_warp_view_t AT,
-                                                                                   const double* __restrict__ ybuf0,
-                                                                                   const double* __restrict__ ybuf1,
-                                                                                   double* __restrict__ buf)
+__global__ void __launch_bounds__(BICSR_THREADS, BICSR_MIN_CTAS) k_transpose_partial(const pdhg_ctl_t* __restrict__ ctl,
+                                                                                     bicsr_view_t AT,
+                                                                                     const double* __restrict__ ybuf0,
+                                                                                     const double* __restrict__ ybuf1,
+                                                                                     double* __restrict__ buf)
 {
   if (!ctl->active) return;
-  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
+  __shared__ double rows[BICSR_WARPS][BICSR_SLOTS];
   const double* yn = ctl->parity ? ybuf0 : ybuf1;
   struct payload_t {};
   auto pre_op = [&](int) { return payload_t{}; };
   auto row_op = [&](int j, double s, const payload_t&) { buf[j] = s; };
-  spmv_warp_rows<payload_t, RPL>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op, make_l2_policies(g_l2_hints).keep);
+  spmv_bicsr_rows<payload_t>(AT, yn, rows[threadIdx.x >> 5], pre_op, row_op, make_l2_policies(g_l2_hints).keep);
 }
 // buf[slot] = sum of `count` per-CTA partials (one CTA, fixed order)
 __global__ void __launch_bounds__(EW_THREADS) k_sum_partials(const pdhg_ctl_t* __restrict__ ctl,
@@ -480,19 +477,18 @@ __global__ void __launch_bounds__(EW_THREADS) k_primal_step_bcast(pdhg_ctl_t* __
 
 // K3p with the reduce-scatter fused in: column j's partial goes straight to its owner's staging row of this rank;
 // stage_peers.p[h] = rank h's stage + rank * nslice.
-template <int RPL>
-__global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? PDHG_MIN_CTAS : 4) k_transpose_partial_scatter(pdhg_ctl_t* __restrict__ ctl,
-                                                                                           csr_warp_view_t AT,
-                                                                                           const double* __restrict__ ybuf0,
-                                                                                           const double* __restrict__ ybuf1,
-                                                                                           peer_ptrs_t stage_peers,
-                                                                                           int nslice,
-                                                                                           peer_flags_t flags,
-                                                                                           int world,
-                                                                                           int rank)
+__global__ void __launch_bounds__(BICSR_THREADS, BICSR_MIN_CTAS) k_transpose_partial_scatter(pdhg_ctl_t* __restrict__ ctl,
+                                                                                             bicsr_view_t AT,
+                                                                                             const double* __restrict__ ybuf0,
+                                                                                             const double* __restrict__ ybuf1,
+                                                                                             peer_ptrs_t stage_peers,
+                                                                                             int nslice,
+                                                                                             peer_flags_t flags,
+                                                                                             int world,
+                                                                                             int rank)
 {
   if (!ctl->active) return;
-  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
+  __shared__ double rows[BICSR_WARPS][BICSR_SLOTS];
   const unsigned long long epoch = (unsigned long long)ctl->attempts + 1ull;
   const double* yn               = ctl->parity ? ybuf0 : ybuf1;
   struct payload_t {};
@@ -505,7 +501,7 @@ __global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? PDHG_MIN_CTAS : 4) k_
       if (h == r) base = stage_peers.p[r];
     base[j - h * nslice] = s;
   };
-  spmv_warp_rows<payload_t, RPL>(AT, yn, prod[threadIdx.x >> 5], pre_op, row_op, make_l2_policies(g_l2_hints).keep);
+  spmv_bicsr_rows<payload_t>(AT, yn, rows[threadIdx.x >> 5], pre_op, row_op, make_l2_policies(g_l2_hints).keep);
   peer_signal_grid_done(&ctl->ticket[2], flags, world, DIST_FLAG_PARTIAL + rank, epoch);
 }
 
@@ -587,65 +583,29 @@ __global__ void k_step_rule_gather(pdhg_ctl_t* __restrict__ ctl, const double* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// L2 warm-up of the vector an SpMV is about to gather from.  A gather that misses L2 costs the DRAM a row activation for
-// one 32-byte sector; the same bytes read sequentially cost ~1/20 of that (pages stay open).  The vector (or the column
-// block's slice of it) is therefore pulled into L2 by a sequential sweep right before the gathers start: +8 bytes per
-// vector element of DRAM reads, in exchange for gathers that hit.  mode 1: 16-byte loads (evict-last), mode 2:
-// prefetch.global.L2::evict_last per 128-byte line.
-//   pick_candidate as in k_block_pass: 0 -> x0, 1 -> the candidate dual y' = parity ? x0 : x1
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EW_THREADS) k_l2_warm(const pdhg_ctl_t* __restrict__ ctl,
-                                                        const double* __restrict__ x0,
-                                                        const double* __restrict__ x1,
-                                                        int pick_candidate,
-                                                        size_t first,
-                                                        size_t count,
-                                                        int mode)
-{
-  if (ctl != nullptr && !ctl->active) return;
-  const double* x = (pick_candidate ? (ctl->parity ? x0 : x1) : x0) + first;
-  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
-  if (mode == 2) {
-    for (size_t i = tid * 16; i < count; i += nthr * 16)
-      asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(x + i));
-    return;
-  }
-  unsigned long long keep;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-  const size_t head = ((16 - ((size_t)x & 15)) & 15) / 8;  // doubles before the first 16-byte boundary
-  double a, b, acc = 0.0;
-  for (size_t i = head + tid * 2; i + 1 < count; i += nthr * 2) {
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(a), "=d"(b) : "l"(x + i), "l"(keep));
-    acc += a + b;
-  }
-  if (acc == 1.2345e-300) asm volatile("trap;");  // keeps the loads alive
-}
-
-// ---------------------------------------------------------------------------------------------
 // Gather blocking (large LPs).  When the vector an SpMV gathers from is much larger than what stays in L2 (80 MB at
 // configs[3] against a 126 MB L2 that also sees ~2 GB of streams per kernel), ncu shows the fused kernels DRAM-bound
 // at 2.4x their algorithmic bytes: every gathered double drags a 32-byte sector in from HBM (profiles/r1).  The
 // host then splits the matrix by COLUMN blocks whose slice of the gathered vector is L2-sized (csr_transpose.cu),
-// and K2 / K3 become   B x k_block_pass (t += A_b * x, payload-free, wide warp blocks)  +  one element-wise epilogue
-// (the row_op of the fused kernel).  Rows keep their entry order inside and across blocks and every pass continues
-// the row's running sum, so t is the same left-to-right sum the fused kernel forms.
+// and K2 / K3 become   (B - 1) x k_block_pass (t += A_b * x, payload-free)  +  the fused kernel on the LAST block with
+// INIT = true (its row sums start from t, its row epilogue is the step's).  Rows keep their entry order inside and across
+// blocks; the result is t_0 + t_1 + ... in block order.
 // ---------------------------------------------------------------------------------------------
 // t[r] = (first ? 0 : t[r]) + sum over the entries of row r in this column block.
 //   pick_candidate = 0: x = x0;  1: x = the candidate dual y' = parity ? x0 : x1  (K3).
 //   wait_flags: peer transport only, first pass of K2 (the xbar slices of the other ranks must have landed).
-template <int RPL>
-__global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? PDHG_MIN_CTAS : 4) k_block_pass(const pdhg_ctl_t* __restrict__ ctl,
-                                                                                          csr_warp_view_t Ab,
-                                                                                          const double* __restrict__ x0,
-                                                                                          const double* __restrict__ x1,
-                                                                                          int pick_candidate,
-                                                                                          double* __restrict__ t,
-                                                                                          int first,
-                                                                                          const unsigned long long* wait_flags,
-                                                                                          int n_wait)
+__global__ void __launch_bounds__(BICSR_THREADS, BICSR_MIN_CTAS) k_block_pass(const pdhg_ctl_t* __restrict__ ctl,
+                                                                              bicsr_view_t Ab,
+                                                                              const double* __restrict__ x0,
+                                                                              const double* __restrict__ x1,
+                                                                              int pick_candidate,
+                                                                              double* __restrict__ t,
+                                                                              int first,
+                                                                              const unsigned long long* wait_flags,
+                                                                              int n_wait)
 {
   if (!ctl->active) return;
-  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
+  __shared__ double rows[BICSR_WARPS][BICSR_SLOTS];
   if (wait_flags) peer_wait(wait_flags, n_wait, (unsigned long long)ctl->attempts + 1ull);
   const double* x       = pick_candidate ? (ctl->parity ? x0 : x1) : x0;
   const l2_policy_t pol = make_l2_policies(g_l2_hints);
@@ -658,80 +618,7 @@ __global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? PDHG_MIN_CTAS : 4) k_
     return p;
   };
   auto row_op = [&](int r, double s, const payload_t&) { st_l2(t + r, s, pol.stream); };
-  spmv_warp_rows<payload_t, RPL, true>(Ab, x, prod[threadIdx.x >> 5], pre_op, row_op, gather_policy(pol));
-}
-
-// K2 epilogue on t = A * xbar (the row_op of k_dual_step, element-wise).
-__global__ void __launch_bounds__(EW_THREADS) k_dual_epilogue(const pdhg_ctl_t* __restrict__ ctl,
-                                                              int m,
-                                                              const double* __restrict__ t,
-                                                              double* __restrict__ ybuf0,
-                                                              double* __restrict__ ybuf1,
-                                                              const double* __restrict__ lc,
-                                                              const double* __restrict__ uc,
-                                                              double* __restrict__ sum_y,
-                                                              double* __restrict__ part_dy2)
-{
-  if (!ctl->active) return;
-  __shared__ double red[32];
-  const int cur         = ctl->parity;
-  const double* y       = cur ? ybuf1 : ybuf0;
-  double* yn            = cur ? ybuf0 : ybuf1;
-  const double sigma    = ctl->sigma;
-  const bool pending    = ctl->pending_avg != 0;
-  const double w        = ctl->pending_weight;
-  const l2_policy_t pol = make_l2_policies(g_l2_hints);
-  double dy2            = 0.0;
-  const int stride      = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
-    const double yi = y[i];
-    if (pending) sum_y[i] = sum_y[i] + w * yi;
-    double next      = yi - (sigma * ld_l2(t + i, pol.stream));
-    const double low = next + sigma * ld_stream(lc + i);
-    const double up  = next + sigma * ld_stream(uc + i);
-    next             = fmax(low, fmin(up, 0.0));
-    st_l2(yn + i, next, pol.keep);
-    const double d = next - yi;
-    dy2 += d * d;
-  }
-  const double tot = block_reduce(dy2, red);
-  if (threadIdx.x == 0) part_dy2[blockIdx.x] = tot;
-}
-
-// K3 epilogue on t = A^T * y' (the row_op of k_transpose_step + the step rule in the last CTA).
-__global__ void __launch_bounds__(EW_THREADS) k_transpose_epilogue(pdhg_ctl_t* __restrict__ ctl,
-                                                                   int n,
-                                                                   const double* __restrict__ t,
-                                                                   const double* __restrict__ xbuf0,
-                                                                   const double* __restrict__ xbuf1,
-                                                                   double* __restrict__ aty0,
-                                                                   double* __restrict__ aty1,
-                                                                   double* __restrict__ parts,
-                                                                   const double* __restrict__ part_dy2,
-                                                                   int n_part_dy2)
-{
-  if (!ctl->active) return;
-  __shared__ double red[32];
-  const int cur     = ctl->parity;
-  const double* x   = cur ? xbuf1 : xbuf0;
-  const double* xn  = cur ? xbuf0 : xbuf1;
-  const double* aty = cur ? aty1 : aty0;
-  double* atyn      = cur ? aty0 : aty1;
-  double acc[2]     = {0.0, 0.0};
-  const int stride  = gridDim.x * blockDim.x;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-    const double s = __ldcs(t + j);
-    atyn[j]        = s;
-    const double d = xn[j] - x[j];
-    acc[0] += d * (s - aty[j]);
-    acc[1] += d * d;
-  }
-  if (!publish_and_elect<2>(acc, parts, &ctl->ticket[0], red)) return;
-  const double interaction = gather_partials(parts, gridDim.x, red);
-  const double dx2         = gather_partials(parts + gridDim.x, gridDim.x, red);
-  const double dy2         = gather_partials(part_dy2, n_part_dy2, red);
-  if (threadIdx.x != 0) return;
-  pdhg_step_rule(ctl, interaction, dx2, dy2);
+  spmv_bicsr_rows<payload_t, true>(Ab, x, rows[threadIdx.x >> 5], pre_op, row_op, pol.keep);
 }
 
 // Peer transport, blocked K3p: t = partial A_g^T y'_g over all n columns -> staging rows of the slice owners.
@@ -789,16 +676,15 @@ __global__ void k_begin_batch(pdhg_ctl_t* ctl, int steps)
 }
 
 // Plain y = A x on the row-block scheme (A^T y after a restart to the average, pdhg.cu:120-134).
-template <int RPL>
-__global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? PDHG_MIN_CTAS : 4) k_spmv(csr_warp_view_t A,
-                                                                      const double* __restrict__ x,
-                                                                      double* __restrict__ out)
+__global__ void __launch_bounds__(BICSR_THREADS, BICSR_MIN_CTAS) k_spmv(bicsr_view_t A,
+                                                                        const double* __restrict__ x,
+                                                                        double* __restrict__ out)
 {
-  __shared__ double prod[WARP_PER_CTA][WARP_NNZ];
+  __shared__ double rows[BICSR_WARPS][BICSR_SLOTS];
   struct payload_t {};
   auto pre_op = [&](int) { return payload_t{}; };
   auto row_op = [&](int i, double s, const payload_t&) { out[i] = s; };
-  spmv_warp_rows<payload_t, RPL>(A, x, prod[threadIdx.x >> 5], pre_op, row_op, make_l2_policies(g_l2_hints).keep);
+  spmv_bicsr_rows<payload_t>(A, x, rows[threadIdx.x >> 5], pre_op, row_op, make_l2_policies(g_l2_hints).keep);
 }
 
 // =============================================================================================
@@ -903,84 +789,8 @@ __device__ __forceinline__ void eval_finalize(pdhg_ctl_t* ctl, const double* par
   }
 }
 
-// T1: rows of A.  parts layout: 6 x gridDim.x = {viol^2, y-part of dual objective, ||y||^2} x {cur, avg}
-__global__ void __launch_bounds__(SPMV_THREADS) k_eval_rows(csr_view_t A,
-                                                            const double* __restrict__ x_cur,
-                                                            const double* __restrict__ x_avg,
-                                                            const double* __restrict__ y_cur,
-                                                            const double* __restrict__ y_avg,
-                                                            const double* __restrict__ lc,
-                                                            const double* __restrict__ uc,
-                                                            double* __restrict__ parts)
-{
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  auto& sm      = *reinterpret_cast<spmv_smem_t<2, EVAL_STAGES>*>(smem_raw);
-  double* red   = sm.red;
-  double acc[6] = {0, 0, 0, 0, 0, 0};
-  struct payload_t {
-    double lo, hi, y0, y1;
-  };
-  auto pre_op = [&](int i) { return payload_t{lc[i], uc[i], y_cur[i], y_avg[i]}; };
-  auto row_op = [&](int i, const double (&s)[2], const payload_t& p) {
-    const double lo = p.lo, hi = p.hi;
-    const double yv[2] = {p.y0, p.y1};
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      // utils.cuh:166-178
-      const double viol = s[v] < lo ? lo - s[v] : (s[v] > hi ? s[v] - hi : 0.0);
-      acc[v] += viol * viol;
-      acc[2 + v] += bound_value_product(yv[v], lo, hi);
-      acc[4 + v] += yv[v] * yv[v];
-    }
-  };
-  const double* xs[2] = {x_cur, x_avg};
-  spmv_pipeline<2, EVAL_STAGES, payload_t>(A, xs, sm, pre_op, row_op);
-#pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    const double t = block_reduce(acc[q], red);
-    if (threadIdx.x == 0) parts[q * gridDim.x + blockIdx.x] = t;
-  }
-}
-
-// T2: rows of A^T + final scalars.  parts layout: 8 x gridDim.x =
-// {||g - rc||^2, rc-part of dual objective, c.x, ||x||^2} x {cur, avg}
-__global__ void __launch_bounds__(SPMV_THREADS) k_eval_cols(pdhg_ctl_t* __restrict__ ctl,
-                                                            csr_view_t AT,
-                                                            const double* __restrict__ x_cur,
-                                                            const double* __restrict__ x_avg,
-                                                            const double* __restrict__ y_cur,
-                                                            const double* __restrict__ y_avg,
-                                                            const double* __restrict__ c,
-                                                            const double* __restrict__ l,
-                                                            const double* __restrict__ u,
-                                                            double* __restrict__ rc_cur,
-                                                            double* __restrict__ rc_avg,
-                                                            double* __restrict__ parts,
-                                                            const double* __restrict__ parts_rows,
-                                                            int n_parts_rows,
-                                                            eval_consts_t k,
-                                                            eval_t* __restrict__ out)  // out[0] current, out[1] average
-{
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  auto& sm      = *reinterpret_cast<spmv_smem_t<2, EVAL_STAGES>*>(smem_raw);
-  double* red   = sm.red;
-  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  struct payload_t {
-    double c, lo, hi, x0, x1;
-  };
-  auto pre_op = [&](int j) { return payload_t{c[j], l[j], u[j], x_cur[j], x_avg[j]}; };
-  auto row_op = [&](int j, const double (&s)[2], const payload_t& p) {
-    const double xv[2] = {p.x0, p.x1};
-    eval_column(j, s, p.c, p.lo, p.hi, xv, k.reduced_cost_rule, rc_cur, rc_avg, acc);
-  };
-  const double* ys[2] = {y_cur, y_avg};
-  spmv_pipeline<2, EVAL_STAGES, payload_t>(AT, ys, sm, pre_op, row_op);
-
-  if (!publish_and_elect<8>(acc, parts, &ctl->ticket[1], red)) return;
-  eval_finalize(ctl, parts, parts_rows, n_parts_rows, k, out, red);
-}
-
-// Row math of T1 on precomputed products ax_cur = A x_cur, ax_avg = A x_avg (element-wise; same parts layout as k_eval_rows).
+// Row math of the evaluation on precomputed products ax_cur = A x_cur, ax_avg = A x_avg (element-wise).
+// parts layout: 6 x gridDim.x = {viol^2, y-part of dual objective, ||y||^2} x {cur, avg}
 __global__ void __launch_bounds__(EW_THREADS) k_eval_rows_from_ax(int m,
                                                                   const double* __restrict__ ax_cur,
                                                                   const double* __restrict__ ax_avg,
@@ -1035,7 +845,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_max_partials(const double* __res
   }
 }
 
-// A^T y (current, average) precomputed (all-reduced in the row-sharded mode): same column math as T2, element-wise.
+// Column math of the evaluation on precomputed A^T y (current, average; all-reduced in the row-sharded mode) + final scalars.
+// parts layout: 8 x gridDim.x = {||g - rc||^2, rc-part of dual objective, c.x, ||x||^2} x {cur, avg}
 __global__ void __launch_bounds__(EW_THREADS) k_eval_cols_from_aty(pdhg_ctl_t* __restrict__ ctl,
                                                                    int n,
                                                                    const double* __restrict__ aty_cur,

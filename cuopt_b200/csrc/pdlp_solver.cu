@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <atomic>
 #include <map>
@@ -33,41 +34,46 @@ namespace cuopt_b200 {
 
 namespace {
 
+// Block-interleaved storage of a matrix (spmv_bicsr.cuh): what every SpMV kernel reads.
+struct bicsr_dev_t {
+  int n_std = 0, n_blk = 0;
+  dvec<int2> desc;
+  dvec<unsigned short> row_slot;
+  dvec<int> idx;
+  dvec<double> val;
+};
+
+// A matrix on the device: plain CSR (setup kernels: scaling statistics, transpose, column split; long rows of the SpMV)
+// + its block-interleaved form (all SpMV kernels).
 struct csr_dev_t {
-  int rows = 0, cols = 0, nnz = 0, n_blocks = 0, n_wb = 0, n_wb_wide = 0;
+  int rows = 0, cols = 0, nnz = 0;
   dvec<int> off, idx;
   dvec<double> val;
-  dvec<int4> blk;    // CTA row blocks (TMA pipeline of the evaluation kernels)
-  dvec<int2> wdesc;  // warp row blocks (hot PDHG kernels)
-  dvec<int2> wdesc_wide;  // <= 256 rows per block, only cut for very sparse matrices (spmv_warp.cuh, RPL = 8)
-  bool wide() const { return n_wb_wide > 0; }
-  csr_warp_view_t warp_view_wide() const
-  {
-    return csr_warp_view_t{off_ptr(), idx_ptr(), val.data(), n_wb_wide,
-                           structure ? structure->wdesc_wide.data() : wdesc_wide.data()};
-  }
-  const csr_dev_t* structure = nullptr;  // scaled copies share offsets / indices / row blocks with the original
+  bicsr_dev_t bi;
+  const csr_dev_t* structure = nullptr;  // scaled copies share offsets / indices / block structure with the original
   const int* off_ptr() const { return structure ? structure->off.data() : off.data(); }
   const int* idx_ptr() const { return structure ? structure->idx.data() : idx.data(); }
-  const int4* blk_ptr() const { return structure ? structure->blk.data() : blk.data(); }
-  csr_view_t view() const { return csr_view_t{rows, off_ptr(), idx_ptr(), val.data(), n_blocks, blk_ptr()}; }
-  csr_warp_view_t warp_view() const
+  const bicsr_dev_t& bi_structure() const { return structure ? structure->bi : bi; }
+  int n_blk() const { return bi_structure().n_blk; }
+  bicsr_view_t view() const
   {
-    return csr_warp_view_t{off_ptr(), idx_ptr(), val.data(), n_wb, structure ? structure->wdesc.data() : wdesc.data()};
+    const bicsr_dev_t& s = bi_structure();
+    return bicsr_view_t{s.desc.data(), s.row_slot.data(), s.idx.data(), bi.val.data(), s.n_std, s.n_blk,
+                        off_ptr(),     idx_ptr(),         val.data()};
   }
   // same sparsity pattern, own values (device-to-device copy)
   void alias_structure_copy_values(const csr_dev_t& o, cudaStream_t s)
   {
-    rows = o.rows; cols = o.cols; nnz = o.nnz; n_blocks = o.n_blocks; n_wb = o.n_wb; n_wb_wide = o.n_wb_wide;
+    rows = o.rows; cols = o.cols; nnz = o.nnz;
     structure = &o;
     val.copy_from(o.val, s);
   }
 };
 
-// The greedy cuts below are sequential in nature; at 10M rows and a dozen schedules per solve they were ~0.5 s of
-// host time.  Rows are therefore cut in independent segments of SCHEDULE_SEGMENT rows (a block never spans a segment
-// boundary) that worker threads process in parallel; the segment results are concatenated in order, so the schedule
-// is the same run to run and independent of the thread count.
+// The greedy cut below is sequential in nature; at 10M rows and several matrices per solve it was ~0.5 s of host time.
+// Rows are therefore cut in independent segments of SCHEDULE_SEGMENT rows (a block never spans a segment boundary) that
+// worker threads process in parallel; the segment results are concatenated in order, so the cut is the same run to run
+// and independent of the thread count.
 constexpr int SCHEDULE_SEGMENT = 1 << 16;
 template <typename T, typename F>
 std::vector<T> cut_in_segments(int rows, F cut_segment)
@@ -95,84 +101,70 @@ std::vector<T> cut_in_segments(int rows, F cut_segment)
   return all;
 }
 
-// Cut consecutive rows into blocks of <= SPMV_NNZ nonzeros and <= SPMV_ROWS rows; a longer row is a block of its own.
-std::vector<int4> build_row_blocks(const std::vector<int>& off)
+// Cuts the rows into BICSR blocks (whole consecutive rows, <= 256 entries, <= 256 rows; a longer row is a long-row block)
+// from HOST row offsets, uploads the descriptors and fills the interleaved arrays on the device from d's plain CSR.
+void build_bicsr(csr_dev_t& d, const std::vector<int>& off, cudaStream_t s, int sms)
 {
   const int all_rows = (int)off.size() - 1;
-  return cut_in_segments<int4>(all_rows, [&](int r, int rows, std::vector<int4>& blocks) {
-  while (r < rows) {
-    const int lo = off[r];
-    int r1       = r;
-    if (off[r + 1] - lo > SPMV_NNZ) {
-      r1 = r + 1;
-    } else {
-      while (r1 < rows && off[r1 + 1] - lo <= SPMV_NNZ && (r1 - r) < SPMV_ROWS) ++r1;
+  constexpr int LONG = (int)0x80000000u;
+  std::vector<int2> cut = cut_in_segments<int2>(all_rows, [&](int r, int rows, std::vector<int2>& out) {
+    while (r < rows) {
+      const int lo = off[r];
+      if (off[r + 1] - lo > BICSR_SLOTS) {
+        out.push_back(make_int2(r | LONG, r + 1));
+        ++r;
+        continue;
+      }
+      int r1 = r;
+      while (r1 < rows && off[r1 + 1] - lo <= BICSR_SLOTS && (r1 - r) < BICSR_MAX_ROWS) ++r1;
+      out.push_back(make_int2(r, r1));
+      r = r1;
     }
-    blocks.push_back(make_int4(r, r1, lo, off[r1]));
-    r = r1;
-  }
   });
-}
-
-// Warp row blocks for the hot kernels: consecutive rows with <= WARP_NNZ nonzeros and <= max_rows rows (32, or
-// 32 * WARP_WIDE_RPL for the wide schedule); a longer row is a block of its own.  Returns n_wb + 1 descriptors
-// {first row, first nnz}.
-std::vector<int2> build_warp_blocks(const std::vector<int>& off, int max_rows = 32)
-{
-  const int all_rows = (int)off.size() - 1;
-  std::vector<int2> wd = cut_in_segments<int2>(all_rows, [&](int r, int rows, std::vector<int2>& wd) {
-  while (r < rows) {
-    const int lo = off[r];
-    int r1       = r;
-    if (off[r + 1] - lo > WARP_NNZ) {
-      r1 = r + 1;
-    } else {
-      while (r1 < rows && off[r1 + 1] - lo <= WARP_NNZ && (r1 - r) < max_rows) ++r1;
-    }
-    wd.push_back(make_int2(r, lo));
-    r = r1;
+  std::vector<int2> desc;
+  desc.reserve(cut.size());
+  for (const int2& c : cut)
+    if (!(c.x & LONG)) desc.push_back(c);
+  const int n_std = (int)desc.size();
+  for (const int2& c : cut)
+    if (c.x & LONG) desc.push_back(make_int2(c.x & ~LONG, c.y));
+  bicsr_dev_t& b = d.bi;
+  b.n_std        = n_std;
+  b.n_blk        = (int)desc.size();
+  b.desc.upload(desc, s);
+  b.row_slot.resize((size_t)std::max(all_rows, 1));
+  b.idx.resize((size_t)std::max(n_std, 1) * BICSR_SLOTS);
+  b.val.resize((size_t)std::max(n_std, 1) * BICSR_SLOTS);
+  if (all_rows > 0) CUOPT_CUDA_TRY(cudaMemsetAsync(b.row_slot.data(), 0xff, (size_t)all_rows * sizeof(unsigned short), s));
+  if (n_std > 0) {
+    const int grid = std::max(1, std::min((n_std + 7) / 8, sms * 8));
+    k_bicsr_fill<<<grid, 256, 0, s>>>(n_std, b.desc.data(), d.off.data(), d.idx.data(), d.val.data(), b.idx.data(),
+                                      b.val.data(), b.row_slot.data());
+    CUOPT_CUDA_TRY(cudaGetLastError());
   }
-  });
-  wd.push_back(make_int2(all_rows, off[all_rows]));
-  return wd;
 }
-
-// Row-block / warp-block schedules from HOST row offsets.
-void upload_warp_schedules(csr_dev_t& d, const std::vector<int>& off, cudaStream_t s);
-
-void upload_schedules(csr_dev_t& d, const std::vector<int>& off, cudaStream_t s)
+// values of a copy that shares the structure of another matrix (after its plain values were scaled)
+void fill_bicsr_values(csr_dev_t& d, cudaStream_t s, int sms)
 {
-  auto blocks = build_row_blocks(off);
-  d.n_blocks  = (int)blocks.size();
-  d.blk.upload(blocks, s);
-  upload_warp_schedules(d, off, s);
-}
-
-// warp blocks only (column blocks of the gather blocking never run the CTA-level evaluation kernels)
-void upload_warp_schedules(csr_dev_t& d, const std::vector<int>& off, cudaStream_t s)
-{
-  auto wblocks = build_warp_blocks(off);
-  d.n_wb       = (int)wblocks.size() - 1;
-  d.wdesc.upload(wblocks, s);
-  const long long rows = (long long)off.size() - 1;
-  d.n_wb_wide          = 0;
-  if (rows > 0 && (long long)off[rows] <= 4 * rows) {  // <= 4 nonzeros per row on average
-    auto wide   = build_warp_blocks(off, 32 * WARP_WIDE_RPL);
-    d.n_wb_wide = (int)wide.size() - 1;
-    d.wdesc_wide.upload(wide, s);
+  const bicsr_dev_t& st = d.bi_structure();
+  d.bi.val.resize((size_t)std::max(st.n_std, 1) * BICSR_SLOTS);
+  if (st.n_std > 0) {
+    const int grid = std::max(1, std::min((st.n_std + 7) / 8, sms * 8));
+    k_bicsr_fill_values<<<grid, 256, 0, s>>>(st.n_std, st.desc.data(), d.off_ptr(), d.val.data(), d.bi.val.data());
+    CUOPT_CUDA_TRY(cudaGetLastError());
   }
 }
 
 void upload_csr(csr_dev_t& d, int rows, int cols, const std::vector<int>& off, const std::vector<int>& idx,
-                const std::vector<double>& val, cudaStream_t s)
+                const std::vector<double>& val, cudaStream_t s, int sms)
 {
   d.rows = rows;
   d.cols = cols;
   d.nnz  = (int)val.size();
-  d.off.upload(off, s, SPMV_TAIL_SLACK);
-  d.idx.upload(idx, s, SPMV_TAIL_SLACK);
-  d.val.upload(val, s, SPMV_TAIL_SLACK);
-  upload_schedules(d, off, s);
+  d.off.upload(off, s);
+  d.idx.upload(idx, s);
+  d.val.upload(val, s);
+  build_bicsr(d, off, s, sms);
 }
 
 }  // namespace
@@ -191,23 +183,21 @@ void csr_split_columns_fill(int rows, const int* off, const int* idx, const doub
 namespace {
 
 // A^T on the device (stable order, see csr_transpose.cu); only its row offsets come back to the host, to cut the schedules.
-void transpose_to(csr_dev_t& t, const csr_dev_t& a, cudaStream_t s)
+void transpose_to(csr_dev_t& t, const csr_dev_t& a, cudaStream_t s, int sms)
 {
   t.rows = a.cols;
   t.cols = a.rows;
   t.nnz  = a.nnz;
-  t.off.resize((size_t)t.rows + 1, SPMV_TAIL_SLACK);
-  t.idx.resize(t.nnz, SPMV_TAIL_SLACK);
-  t.val.resize(t.nnz, SPMV_TAIL_SLACK);
+  t.off.resize((size_t)t.rows + 1);
+  t.idx.resize(t.nnz);
+  t.val.resize(t.nnz);
   csr_transpose_device(a.rows, a.cols, a.nnz, a.off.data(), a.idx.data(), a.val.data(), t.off.data(), t.idx.data(),
                        t.val.data(), s);
   std::vector<int> toff((size_t)t.rows + 1);
   t.off.download(toff.data(), s);
   CUOPT_CUDA_TRY(cudaStreamSynchronize(s));
-  upload_schedules(t, toff, s);
+  build_bicsr(t, toff, s, sms);
 }
-
-constexpr size_t SMEM_EVAL = sizeof(spmv_smem_t<2, EVAL_STAGES>);
 
 int ew_grid(int n, int sms) { return std::max(1, std::min((n + EW_THREADS - 1) / EW_THREADS, sms * 8)); }
 
@@ -256,8 +246,7 @@ struct pdlp_solver_t::impl_t {
   pdhg_ctl_t* h_ctl = nullptr;  // pinned mirrors
   eval_t* h_eval    = nullptr;
   double* h_scalar  = nullptr;
-  int grid_sp = 1, grid_sp_wide = 1, grid_k3p_wide = 1, occ_spmv = 1, occ_spmv_wide = 1;
-  bool eval_tma = false;
+  int occ_spmv = 1;  // resident CTAs per SM of the SpMV kernels (64 registers, 16 KB of shared memory)
   dvec<double> eval_m, eval_n;  // A x (current, average) and, on one GPU, A^T y (current, average)
   dvec<double> part_max;        // per_constraint_residual: per-CTA maxima, rows (2 x grid_m) then columns (2 x grid_n)
   dvec<double> part_infeas;     // infeasibility detection: rows (6 x grid_m) then columns (12 x grid_n)
@@ -281,10 +270,9 @@ struct pdlp_solver_t::impl_t {
   };
   gather_blocks_t blkA, blkAT;
   dvec<double> t_m, t_n;
-  int l2_warm = 0;  // 0 off, 1 sequential loads, 2 prefetch instructions (k_l2_warm); CUOPT_B200_L2_WARM
   size_t gather_block_bytes = 40u << 20;  // measured optimum at configs[3] (profiles/r1/gather_block_sweep_c4.txt)
   int n_part_dy2 = 1;  // CTAs that publish ||dy||^2 partials: grid_k2 (fused K2) or grid_m (blocked K2 epilogue)
-  int grid_k1 = 1, grid_k2 = 1, grid_k3 = 1, grid_er = 1, grid_ec = 1, grid_n = 1, grid_m = 1, grid_misc = 1;
+  int grid_k1 = 1, grid_k2 = 1, grid_k3 = 1, grid_n = 1, grid_m = 1, grid_misc = 1;
   std::map<int, cudaGraphExec_t> graphs;
   bool use_graphs = true;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
@@ -329,6 +317,12 @@ struct pdlp_solver_t::impl_t {
     if (h_eval) cudaFreeHost(h_eval);
     if (h_scalar) cudaFreeHost(h_scalar);
     if (stream) cudaStreamDestroy(stream);
+  }
+
+  // one wave of resident CTAs, or fewer when the matrix has fewer blocks than that (8 warps = 8 blocks per CTA)
+  int spmv_grid(const csr_dev_t& M) const
+  {
+    return std::max(1, std::min((M.n_blk() + BICSR_WARPS - 1) / BICSR_WARPS, sms * occ_spmv));
   }
 
   void sync() { CUOPT_CUDA_TRY(cudaStreamSynchronize(stream)); }
@@ -378,8 +372,8 @@ struct pdlp_solver_t::impl_t {
     for (int i = 0; i < m; ++i)
       if (hlc[i] > huc[i]) throw lp_error(error_type_t::ValidationError, "Constraint lower bound above upper bound");
 
-    upload_csr(A, m, n, p.A_offsets, p.A_indices, p.A_values, stream);
-    transpose_to(AT, A, stream);
+    upload_csr(A, m, n, p.A_offsets, p.A_indices, p.A_values, stream, sms);
+    transpose_to(AT, A, stream, sms);
     As.alias_structure_copy_values(A, stream);
     ATs.alias_structure_copy_values(AT, stream);
     c.upload(hc, stream); l.upload(hl, stream); u.upload(hu, stream); lc.upload(hlc, stream); uc.upload(huc, stream);
@@ -406,48 +400,26 @@ struct pdlp_solver_t::impl_t {
     Dr.resize(m);
     Dc.resize(n);
 
-    // persistent grids: one wave of resident CTAs
-    auto occ_grid = [&](const void* kernel, int blocks, size_t smem) {
-      CUOPT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int per_sm = 1;
-      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPMV_THREADS, smem));
-      return std::max(1, std::min(blocks, sms * std::max(per_sm, 1)));
-    };
-    auto warp_grid = [&](const void* kernel, int n_wb) {
-      int per_sm = 1;
-      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARP_THREADS, 0));
-      const int ctas = (n_wb + WARP_PER_CTA - 1) / WARP_PER_CTA;
-      return std::max(1, std::min(ctas, sms * std::max(per_sm, 1)));
-    };
-    grid_k2   = warp_grid((const void*)k_dual_step, As.n_wb);
-    grid_k3   = warp_grid((const void*)k_transpose_step, ATs.n_wb);
-    grid_sp   = warp_grid((const void*)k_spmv<1>, ATs.n_wb);
-    if (ATs.wide()) {
-      grid_sp_wide  = warp_grid((const void*)k_spmv<WARP_WIDE_RPL>, ATs.n_wb_wide);
-      grid_k3p_wide = warp_grid((const void*)k_transpose_partial<WARP_WIDE_RPL>, ATs.n_wb_wide);
+    // persistent grids: one wave of resident CTAs (the SpMV kernels all share the core's footprint; the fused K2 / K3
+    // carry the largest payload, so their occupancy bounds the others')
+    {
+      int o2 = 1, o3 = 1;
+      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, (const void*)k_dual_step<true>, BICSR_THREADS, 0));
+      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, (const void*)k_transpose_step<true>, BICSR_THREADS, 0));
+      occ_spmv = std::max(1, std::min(o2, o3));
     }
-    grid_er   = occ_grid((const void*)k_eval_rows, A.n_blocks, SMEM_EVAL);
-    grid_ec   = occ_grid((const void*)k_eval_cols, AT.n_blocks, SMEM_EVAL);
+    grid_k2   = spmv_grid(As);
+    grid_k3   = spmv_grid(ATs);
     grid_n    = ew_grid(n, sms);
     grid_m    = ew_grid(m, sms);
     grid_k1   = grid_n;
     grid_misc = ew_grid(std::max(n, m), sms);
-    part_dy2.resize(std::max(grid_k2, grid_m));
+    part_dy2.resize((size_t)std::max({grid_k2, grid_m, sms * 16}));
     n_part_dy2 = grid_k2;
     // size of the slice of the gathered vector one column block may span (0 = never block); bytes, for the tests too
     if (const char* e = std::getenv("CUOPT_B200_GATHER_BLOCK_BYTES")) gather_block_bytes = (size_t)std::atoll(e);
-    if (const char* e = std::getenv("CUOPT_B200_L2_WARM")) l2_warm = std::atoi(e);
-    {
-      const char* e = std::getenv("CUOPT_B200_GATHER_LDG");
-      const int on  = (e != nullptr && e[0] == '1') ? 1 : 0;
-      CUOPT_CUDA_TRY(cudaMemcpyToSymbol(g_gather_ldg, &on, sizeof(int)));
-    }
-    part_k3.resize(2 * (size_t)std::max(grid_k3, grid_n));
-    part_rows.resize(6 * (size_t)std::max(grid_er, grid_m));
-    // evaluation of the iterates: four SpMVs on the warp-block core + element-wise row / column math (default), or the
-    // two CTA-level TMA-pipeline kernels that handle two vectors per pass (CUOPT_B200_EVAL=tma; measured 3x slower at
-    // configs[3], profiles/r1/launch_list_c4_bench.md)
-    if (const char* e = std::getenv("CUOPT_B200_EVAL")) eval_tma = std::string(e) == "tma";
+    part_k3.resize(2 * (size_t)std::max({grid_k3, grid_n, sms * 16}));
+    part_rows.resize(6 * (size_t)grid_m);
     if (hp.restart_strategy == 2) {
       tr_enabled = true;
       {
@@ -465,20 +437,12 @@ struct pdlp_solver_t::impl_t {
     if (st.detect_infeasibility) {
       if (sharded())
         throw lp_error(error_type_t::ValidationError, "infeasibility_detection is not available in multi-GPU solves yet");
-      eval_tma = false;  // needs the four products of the element-wise evaluation path
       part_infeas.resize(6 * (size_t)grid_m + 12 * (size_t)grid_n);
     }
-    if (st.per_constraint_residual) {  // the linf residuals are only implemented on the element-wise evaluation path
-      eval_tma = false;
-      part_max.resize(2 * (size_t)std::max(grid_m, grid_n) * 2);
-    }
-    if (!eval_tma) {
-      eval_m.resize(2 * (size_t)m);
-      if (!sharded()) eval_n.resize(2 * (size_t)n);
-    }
-    CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_spmv, (const void*)k_spmv<1>, WARP_THREADS, 0));
-    CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_spmv_wide, (const void*)k_spmv<WARP_WIDE_RPL>, WARP_THREADS, 0));
-    part_cols.resize(8 * (size_t)std::max(grid_ec, grid_n));
+    if (st.per_constraint_residual) part_max.resize(2 * (size_t)std::max(grid_m, grid_n) * 2);
+    eval_m.resize(2 * (size_t)m);
+    if (!sharded()) eval_n.resize(2 * (size_t)n);
+    part_cols.resize(8 * (size_t)grid_n);
     part_misc.resize(2 * (size_t)std::max(grid_misc, ew_grid(nnz, sms)));
     d_scalar.resize(12);
     if (sharded()) setup_transport();
@@ -620,9 +584,11 @@ struct pdlp_solver_t::impl_t {
     if (hp.compute_initial_step_size_before_scaling) step = initial_step_size(A);
     if (hp.compute_initial_primal_weight_before_scaling) weight = initial_primal_weight(c, lc, uc);
     scale_problem();
+    fill_bicsr_values(As, stream, sms);
+    fill_bicsr_values(ATs, stream, sms);
     build_gather_blocks(As, blkA, t_m);
     build_gather_blocks(ATs, blkAT, t_n);
-    n_part_dy2 = blkA.on() ? grid_m : grid_k2;
+    n_part_dy2 = blkA.on() ? blkA.grid[blkA.B - 1] : grid_k2;  // CTAs of the kernel that runs the dual row epilogue
     if (!hp.compute_initial_step_size_before_scaling) step = initial_step_size(As);
     if (!hp.compute_initial_primal_weight_before_scaling) weight = initial_primal_weight(cs, lcs, ucs);
 
@@ -747,14 +713,14 @@ struct pdlp_solver_t::impl_t {
     for (int b = 0; b < B; ++b) {
       g.blk[b].rows = M.rows;
       g.blk[b].cols = M.cols;
-      g.blk[b].off.resize((size_t)M.rows + 1, SPMV_TAIL_SLACK);
+      g.blk[b].off.resize((size_t)M.rows + 1);
       offs[b] = g.blk[b].off.data();
     }
     csr_split_columns_offsets(M.rows, M.off_ptr(), M.idx_ptr(), g.width, B, offs.data(), nnz_b.data(), stream);
     for (int b = 0; b < B; ++b) {
       g.blk[b].nnz = nnz_b[b];
-      g.blk[b].idx.resize((size_t)nnz_b[b], SPMV_TAIL_SLACK);
-      g.blk[b].val.resize((size_t)nnz_b[b], SPMV_TAIL_SLACK);
+      g.blk[b].idx.resize((size_t)nnz_b[b]);
+      g.blk[b].val.resize((size_t)nnz_b[b]);
       idxs[b] = g.blk[b].idx.data();
       vals[b] = g.blk[b].val.data();
     }
@@ -762,81 +728,61 @@ struct pdlp_solver_t::impl_t {
                            stream);
     std::vector<int> hoff((size_t)M.rows + 1);
     g.grid.resize(B);
-    auto grid_for = [&](const void* kernel, int n_wb) {
-      int per_sm = 1;
-      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARP_THREADS, 0));
-      return std::max(1, std::min((n_wb + WARP_PER_CTA - 1) / WARP_PER_CTA, sms * std::max(per_sm, 1)));
-    };
     for (int b = 0; b < B; ++b) {
       g.blk[b].off.download(hoff.data(), stream);
       sync();
-      upload_warp_schedules(g.blk[b], hoff, stream);
-      g.grid[b] = g.blk[b].wide() ? grid_for((const void*)k_block_pass<WARP_WIDE_RPL>, g.blk[b].n_wb_wide)
-                                  : grid_for((const void*)k_block_pass<1>, g.blk[b].n_wb);
+      build_bicsr(g.blk[b], hoff, stream, sms);
+      g.grid[b] = spmv_grid(g.blk[b]);
     }
     t.resize((size_t)M.rows);
     t.zero(stream);
   }
-  // sequential sweep that pulls [first, first + count) of the vector the next SpMV gathers from into L2 (k_l2_warm)
-  void launch_l2_warm(const double* x0, const double* x1, int pick_candidate, size_t first, size_t count)
+  // t (+)= M_b * x for the column blocks [0, count), in block order
+  void launch_block_passes(const gather_blocks_t& g, int count, const double* x0, const double* x1, int pick_candidate,
+                           double* t, const unsigned long long* wait_flags, int n_wait)
   {
-    if (!l2_warm || count == 0) return;
-    const size_t per_thread = l2_warm == 2 ? 16 : 2;
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((count / per_thread + EW_THREADS - 1) / EW_THREADS, (size_t)sms * 8));
-    k_l2_warm<<<grid, EW_THREADS, 0, stream>>>(d_ctl.data(), x0, x1, pick_candidate, first, count, l2_warm);
-  }
-  // t (+)= M_b * x for every column block, in block order
-  void launch_block_passes(const gather_blocks_t& g, const double* x0, const double* x1, int pick_candidate, double* t,
-                           const unsigned long long* wait_flags, int n_wait)
-  {
-    for (int b = 0; b < g.B; ++b) {
+    for (int b = 0; b < count; ++b) {
       const csr_dev_t& M = g.blk[b];
-      if (wait_flags == nullptr) {
-        const size_t first = (size_t)b * g.width;
-        launch_l2_warm(x0, x1, pick_candidate, first, std::min<size_t>(g.width, (size_t)M.cols - first));
-      }
-      const unsigned long long* wf = b == 0 ? wait_flags : nullptr;
-      if (M.wide())
-        k_block_pass<WARP_WIDE_RPL><<<g.grid[b], WARP_THREADS, 0, stream>>>(d_ctl.data(), M.warp_view_wide(), x0, x1,
-                                                                            pick_candidate, t, b == 0, wf, n_wait);
-      else
-        k_block_pass<1><<<g.grid[b], WARP_THREADS, 0, stream>>>(d_ctl.data(), M.warp_view(), x0, x1, pick_candidate, t,
-                                                                b == 0, wf, n_wait);
+      k_block_pass<<<g.grid[b], BICSR_THREADS, 0, stream>>>(d_ctl.data(), M.view(), x0, x1, pick_candidate, t, b == 0,
+                                                            b == 0 ? wait_flags : nullptr, n_wait);
     }
   }
-  // K2: fused, or column-blocked passes + element-wise epilogue.  wait_flags: peer transport (xbar slices of the peers)
+  // K2: one fused kernel; with gather blocking (B - 1) payload-free passes over the first column blocks, then the fused kernel
+  // on the last block continuing their running sum.  wait_flags: peer transport (xbar slices of the peers)
   void enqueue_k2(const unsigned long long* wait_flags, int n_wait)
   {
     if (!blkA.on()) {
-      if (wait_flags == nullptr) launch_l2_warm(xbar.data(), xbar.data(), 0, 0, (size_t)n);
-      k_dual_step<<<grid_k2, WARP_THREADS, 0, stream>>>(d_ctl.data(), As.warp_view(), xbar.data(), ybuf[0].data(),
-                                                        ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(), part_dy2.data(),
-                                                        wait_flags, n_wait);
+      k_dual_step<false><<<grid_k2, BICSR_THREADS, 0, stream>>>(d_ctl.data(), As.view(), xbar.data(), ybuf[0].data(),
+                                                                ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(),
+                                                                part_dy2.data(), wait_flags, n_wait, nullptr);
       return;
     }
-    launch_block_passes(blkA, xbar.data(), xbar.data(), 0, t_m.data(), wait_flags, n_wait);
-    k_dual_epilogue<<<grid_m, EW_THREADS, 0, stream>>>(d_ctl.data(), m, t_m.data(), ybuf[0].data(), ybuf[1].data(), lcs.data(),
-                                                       ucs.data(), sum_y.data(), part_dy2.data());
+    launch_block_passes(blkA, blkA.B - 1, xbar.data(), xbar.data(), 0, t_m.data(), wait_flags, n_wait);
+    const csr_dev_t& L = blkA.blk[blkA.B - 1];
+    k_dual_step<true><<<blkA.grid[blkA.B - 1], BICSR_THREADS, 0, stream>>>(d_ctl.data(), L.view(), xbar.data(), ybuf[0].data(),
+                                                                           ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(),
+                                                                           part_dy2.data(), nullptr, 0, t_m.data());
   }
-  // K3 on one GPU: fused, or column-blocked passes + element-wise epilogue with the step rule
+  // K3 on one GPU: same structure, the step rule runs in the last CTA of the fused kernel
   void enqueue_k3()
   {
     if (!blkAT.on()) {
-      launch_l2_warm(ybuf[0].data(), ybuf[1].data(), 1, 0, (size_t)m);
-      k_transpose_step<<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(),
-                                                             xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
-                                                             atybuf[1].data(), part_k3.data(), part_dy2.data(), n_part_dy2);
+      k_transpose_step<false><<<grid_k3, BICSR_THREADS, 0, stream>>>(d_ctl.data(), ATs.view(), ybuf[0].data(), ybuf[1].data(),
+                                                                     xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
+                                                                     atybuf[1].data(), part_k3.data(), part_dy2.data(),
+                                                                     n_part_dy2, nullptr);
       return;
     }
-    launch_block_passes(blkAT, ybuf[0].data(), ybuf[1].data(), 1, t_n.data(), nullptr, 0);
-    k_transpose_epilogue<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, t_n.data(), xbuf[0].data(), xbuf[1].data(),
-                                                            atybuf[0].data(), atybuf[1].data(), part_k3.data(),
-                                                            part_dy2.data(), n_part_dy2);
+    launch_block_passes(blkAT, blkAT.B - 1, ybuf[0].data(), ybuf[1].data(), 1, t_n.data(), nullptr, 0);
+    const csr_dev_t& L = blkAT.blk[blkAT.B - 1];
+    k_transpose_step<true><<<blkAT.grid[blkAT.B - 1], BICSR_THREADS, 0, stream>>>(
+      d_ctl.data(), L.view(), ybuf[0].data(), ybuf[1].data(), xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
+      atybuf[1].data(), part_k3.data(), part_dy2.data(), n_part_dy2, t_n.data());
   }
   int kernels_per_attempt() const
   {
-    const int k2 = blkA.on() ? blkA.B + 1 : 1;
-    if (!sharded()) return 1 + k2 + (blkAT.on() ? blkAT.B + 1 : 1);
+    const int k2 = blkA.on() ? blkA.B : 1;
+    if (!sharded()) return 1 + k2 + (blkAT.on() ? blkAT.B : 1);
     const int k3p = blkAT.on() ? blkAT.B + (dist_mode == DIST_P2P ? 1 : 0) : 1;
     return 1 + k2 + k3p + (dist_mode == DIST_ALLREDUCE ? 2 : 2);
   }
@@ -845,26 +791,16 @@ struct pdlp_solver_t::impl_t {
   void launch_transpose_partial()
   {
     if (blkAT.on()) {  // the passes accumulate straight into the collective's send buffer
-      launch_block_passes(blkAT, ybuf[0].data(), ybuf[1].data(), 1, dist_buf.data(), nullptr, 0);
+      launch_block_passes(blkAT, blkAT.B, ybuf[0].data(), ybuf[1].data(), 1, dist_buf.data(), nullptr, 0);
       return;
     }
-    if (ATs.wide())
-      k_transpose_partial<WARP_WIDE_RPL><<<grid_k3p_wide, WARP_THREADS, 0, stream>>>(
-        d_ctl.data(), ATs.warp_view_wide(), ybuf[0].data(), ybuf[1].data(), dist_buf.data());
-    else
-      k_transpose_partial<1><<<grid_k3, WARP_THREADS, 0, stream>>>(d_ctl.data(), ATs.warp_view(), ybuf[0].data(),
-                                                                   ybuf[1].data(), dist_buf.data());
+    k_transpose_partial<<<grid_k3, BICSR_THREADS, 0, stream>>>(d_ctl.data(), ATs.view(), ybuf[0].data(), ybuf[1].data(),
+                                                               dist_buf.data());
   }
-  // out = M v on the warp-block scheme
+  // out = M v
   void launch_spmv(const csr_dev_t& M, const double* v, double* out)
   {
-    auto grid = [&](int n_wb, int occ) {
-      return std::max(1, std::min((n_wb + WARP_PER_CTA - 1) / WARP_PER_CTA, sms * std::max(occ, 1)));
-    };
-    if (M.wide())
-      k_spmv<WARP_WIDE_RPL><<<grid(M.n_wb_wide, occ_spmv_wide), WARP_THREADS, 0, stream>>>(M.warp_view_wide(), v, out);
-    else
-      k_spmv<1><<<grid(M.n_wb, occ_spmv), WARP_THREADS, 0, stream>>>(M.warp_view(), v, out);
+    k_spmv<<<spmv_grid(M), BICSR_THREADS, 0, stream>>>(M.view(), v, out);
   }
 
   // scheme (ii): this rank updates only its slice of the primal side (kernel comments in pdlp_kernels.cuh)
@@ -878,14 +814,11 @@ struct pdlp_solver_t::impl_t {
                                                                  p_flags, G, rk);
       enqueue_k2(d_flags.data() + DIST_FLAG_XBAR, G);
       if (blkAT.on()) {
-        launch_block_passes(blkAT, ybuf[0].data(), ybuf[1].data(), 1, t_n.data(), nullptr, 0);
+        launch_block_passes(blkAT, blkAT.B, ybuf[0].data(), ybuf[1].data(), 1, t_n.data(), nullptr, 0);
         k_scatter_partials<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, t_n.data(), p_stage, nslice, p_flags, G, rk);
-      } else if (ATs.wide())
-        k_transpose_partial_scatter<WARP_WIDE_RPL><<<grid_k3p_wide, WARP_THREADS, 0, stream>>>(
-          d_ctl.data(), ATs.warp_view_wide(), ybuf[0].data(), ybuf[1].data(), p_stage, nslice, p_flags, G, rk);
-      else
-        k_transpose_partial_scatter<1><<<grid_k3, WARP_THREADS, 0, stream>>>(
-          d_ctl.data(), ATs.warp_view(), ybuf[0].data(), ybuf[1].data(), p_stage, nslice, p_flags, G, rk);
+      } else
+        k_transpose_partial_scatter<<<grid_k3, BICSR_THREADS, 0, stream>>>(d_ctl.data(), ATs.view(), ybuf[0].data(),
+                                                                          ybuf[1].data(), p_stage, nslice, p_flags, G, rk);
       k_interaction_slice<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, stage.data(), G, (size_t)nslice, x0, x1,
                                                                  a0, a1, part_k3.data(), part_dy2.data(), n_part_dy2,
                                                                  d_flags.data() + DIST_FLAG_PARTIAL, p_scal, p_flags, G, rk);
@@ -1034,26 +967,15 @@ struct pdlp_solver_t::impl_t {
                                                              x_avg.data(), Dc.data());
     k_average_and_unscale<<<grid_m, EW_THREADS, 0, stream>>>(d_ctl.data(), mode, m, ybuf[cur].data(), sum_y.data(),
                                                              y_avg.data(), Dr.data());
-    int n_rows_parts = grid_er;
-    if (eval_tma) {
-      k_eval_rows<<<grid_er, SPMV_THREADS, SMEM_EVAL, stream>>>(A.view(), xbuf[cur].data(), x_avg.data(), ybuf[cur].data(),
-                                                                y_avg.data(), lc.data(), uc.data(), part_rows.data());
-    } else {
-      launch_spmv(A, xbuf[cur].data(), eval_m.data());
-      launch_spmv(A, x_avg.data(), eval_m.data() + m);
-      k_eval_rows_from_ax<<<grid_m, EW_THREADS, 0, stream>>>(m, eval_m.data(), eval_m.data() + m, ybuf[cur].data(),
-                                                             y_avg.data(), lc.data(), uc.data(), part_rows.data(),
-                                                             st.relative_primal_tolerance,
-                                                             st.per_constraint_residual ? part_max.data() : nullptr);
-      n_rows_parts = grid_m;
-      launches += 2;
-    }
-    if (!sharded() && eval_tma) {
-      k_eval_cols<<<grid_ec, SPMV_THREADS, SMEM_EVAL, stream>>>(d_ctl.data(), AT.view(), xbuf[cur].data(), x_avg.data(),
-                                                        ybuf[cur].data(), y_avg.data(), c.data(), l.data(), u.data(),
-                                                        rc_cur.data(), rc_avg.data(), part_cols.data(), part_rows.data(),
-                                                        grid_er, eval_consts(), d_eval.data());
-    } else {
+    launch_spmv(A, xbuf[cur].data(), eval_m.data());
+    launch_spmv(A, x_avg.data(), eval_m.data() + m);
+    k_eval_rows_from_ax<<<grid_m, EW_THREADS, 0, stream>>>(m, eval_m.data(), eval_m.data() + m, ybuf[cur].data(),
+                                                           y_avg.data(), lc.data(), uc.data(), part_rows.data(),
+                                                           st.relative_primal_tolerance,
+                                                           st.per_constraint_residual ? part_max.data() : nullptr);
+    const int n_rows_parts = grid_m;
+    launches += 2;
+    {
       // A^T y for both iterates, then the column math element-wise.  Row-sharded: the six row sums and both products
       // are partial and are combined over the ranks first.
       double* aty2            = sharded() ? dist_buf.data() : eval_n.data();
@@ -1636,26 +1558,19 @@ kernel_profile_t pdlp_solver_t::profile_kernels(int warmup_steps, int reps)
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev[0], ev[1]);
   out.ms_iteration = ms / reps;
-  // the sharded solve's payload-free partial product on this A^T (scratch output), both block schedules
+  // the sharded solve's payload-free partial product on this A^T (scratch output)
   {
     dvec<double> scratch((size_t)s.n);
-    for (int wide = 0; wide < 2; ++wide) {
-      if (wide && !s.ATs.wide()) break;
-      const int g = wide ? s.grid_k3p_wide : s.grid_k3;
-      for (int r = 0; r < reps + 3; ++r) {
-        if (r == 3) cudaEventRecord(ev[0], s.stream);
-        if (wide)
-          k_transpose_partial<WARP_WIDE_RPL><<<g, WARP_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.ATs.warp_view_wide(),
-                                                                              s.ybuf[0].data(), s.ybuf[1].data(), scratch.data());
-        else
-          k_transpose_partial<1><<<g, WARP_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.ATs.warp_view(), s.ybuf[0].data(),
-                                                                   s.ybuf[1].data(), scratch.data());
-      }
-      cudaEventRecord(ev[1], s.stream);
-      cudaEventSynchronize(ev[1]);
-      cudaEventElapsedTime(&ms, ev[0], ev[1]);
-      (wide ? out.ms_transpose_partial_wide : out.ms_transpose_partial) = ms / reps;
+    for (int r = 0; r < reps + 3; ++r) {
+      if (r == 3) cudaEventRecord(ev[0], s.stream);
+      k_transpose_partial<<<s.grid_k3, BICSR_THREADS, 0, s.stream>>>(s.d_ctl.data(), s.ATs.view(), s.ybuf[0].data(),
+                                                                    s.ybuf[1].data(), scratch.data());
     }
+    cudaEventRecord(ev[1], s.stream);
+    cudaEventSynchronize(ev[1]);
+    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    out.ms_transpose_partial      = ms / reps;
+    out.ms_transpose_partial_wide = 0.0;  // the wide schedule of round 1 is gone: one block format serves all densities
     s.check_launch();
   }
   for (auto& e : ev) cudaEventDestroy(e);

@@ -74,7 +74,8 @@ csr_t make_fixed(int rows, int cols, int k, uint64_t seed)
   for (int r = 0; r <= rows; ++r) A.off[r] = r * k;
 #pragma omp parallel for schedule(static)
   for (int r = 0; r < rows; ++r) {
-    uint64_t s = seed * 0x1234567ull + (uint64_t)r * 0x9e3779b97f4a7c15ull;
+    uint64_t s0 = seed * 0x632be59bd9b4e019ull + (uint64_t)r;  // decorrelate the rows: hash the row number first
+    uint64_t s  = splitmix(s0);
     int* c     = A.idx.data() + (size_t)r * k;
     for (int j = 0; j < k; ++j) c[j] = (int)(splitmix(s) % (uint64_t)cols);
     std::sort(c, c + k);

@@ -12,7 +12,119 @@
 //                 memory (slot of the row's last entry) to reach the lane that runs the row epilogue.
 //   gather<U>, stream_gather<U>   rowless ceilings (no reduction at all)
 // nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Icuopt_b200/csrc -Iinclude scripts/spmv_lab.cu -o gpurun_out/spmv_lab
-#include "spmv_warp.cuh"
+#include "pdlp_kernels.cuh"
+
+// ---- the round-1 core (spmv_warp.cuh of round 1), kept here as the baseline the new format is measured against ----
+namespace cuopt_b200 {
+constexpr int WARP_THREADS = 256;                // CTA size of the warp-block kernels
+constexpr int WARP_PER_CTA = WARP_THREADS / 32;
+constexpr int WARP_NNZ     = 256;                // nonzeros per warp block (8 per lane)
+constexpr int WARP_KN      = WARP_NNZ / 32;
+constexpr int WARP_WIDE_RPL = 8;                 // rows per lane of the wide schedule (blocks of <= 256 rows)
+__host__ __device__ constexpr int warp_swz(int e) { return e ^ ((e >> 4) & 7); }
+
+struct csr_warp_view_t {
+  const int* off;
+  const int* idx;
+  const double* val;
+  int n_wb;
+  const int2* wdesc;  // n_wb + 1 entries {first row, first nnz}; entry n_wb = {rows, nnz}
+};
+
+// Walks this warp's blocks (static round robin over all warps of the grid).
+//   pre_op(row)              -> payload P, issued before the matrix loads of the block
+//   row_op(row, sum, P)      exactly once per row, by one lane
+// `pw` = this warp's WARP_NNZ doubles of shared memory.
+// RPL = rows per lane: 1 for the usual blocks of <= 32 rows; 8 for the "wide" schedule (<= 256 rows per block) that the
+// host cuts for very sparse matrices (< 4 nonzeros per row: the transposed row shard A_g^T of a many-GPU solve has
+// n rows but only nnz/G nonzeros), where blocks of 32 rows would leave 7 of the 8 gather slots of every lane idle.
+// INIT: the row sum starts from P::init (a partial sum of the same row over earlier column blocks, see the gather
+// blocking in pdlp_kernels.cuh) instead of 0, so that block after block the additions stay strictly left to right.
+template <typename P, int RPL = 1, bool INIT = false, typename PreOp, typename RowOp>
+__device__ __forceinline__ void spmv_warp_rows(const csr_warp_view_t& A,
+                                               const double* __restrict__ x,
+                                               double* pw,
+                                               PreOp& pre_op,
+                                               RowOp& row_op,
+                                               unsigned long long gather_policy)
+{
+  const int lane   = threadIdx.x & 31;
+  const int gwarp  = blockIdx.x * WARP_PER_CTA + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * WARP_PER_CTA;
+  for (int wb = gwarp; wb < A.n_wb; wb += nwarps) {
+    const int2 d0 = __ldg(A.wdesc + wb), d1 = __ldg(A.wdesc + wb + 1);
+    const int r0 = d0.x, lo = d0.y, r1 = d1.x, hi = d1.y;
+    if (hi - lo > WARP_NNZ) {
+      // one long row: lanes stride over it, fixed xor tree at the end
+      P pl;
+      if (lane == 0) pl = pre_op(r0);
+      double acc = 0.0;
+      for (int e = lo + lane; e < hi; e += 32) acc += ld_stream(A.val + e) * ld_l2(x + ld_stream(A.idx + e), gather_policy);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        if constexpr (INIT) acc = pl.init + acc;  // long rows are tree sums anyway
+        row_op(r0, acc, pl);
+      }
+      continue;
+    }
+    int rs[RPL], re[RPL];
+    P pl[RPL];
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+      const int r = r0 + lane + 32 * q;
+      rs[q] = re[q] = 0;
+      if (r < r1) {
+        rs[q] = __ldg(A.off + r) - lo;
+        re[q] = __ldg(A.off + r + 1) - lo;
+        pl[q] = pre_op(r);
+      }
+    }
+    int c[WARP_KN];
+    double a[WARP_KN];
+#pragma unroll
+    for (int k = 0; k < WARP_KN; ++k) {
+      const int e = lo + lane + 32 * k;
+      c[k]        = e < hi ? ld_stream(A.idx + e) : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < WARP_KN; ++k) {
+      const int e = lo + lane + 32 * k;
+      a[k]        = e < hi ? ld_stream(A.val + e) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < WARP_KN; ++k)
+      if (c[k] >= 0) pw[warp_swz(lane + 32 * k)] = a[k] * ld_l2(x + c[k], gather_policy);
+    __syncwarp();
+    if constexpr (RPL == 1) {
+      if (r0 + lane < r1) {
+        double s = 0.0;
+        if constexpr (INIT) s = pl[0].init;
+        for (int p = rs[0]; p < re[0]; p += 8) {
+          double v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (p + j < re[0]) ? pw[warp_swz(p + j)] : 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s += v[j];
+        }
+        row_op(r0 + lane, s, pl[0]);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) {
+        const int r = r0 + lane + 32 * q;
+        if (r < r1) {
+          double s = 0.0;
+          if constexpr (INIT) s = pl[q].init;
+          for (int p = rs[q]; p < re[q]; ++p) s += pw[warp_swz(p)];
+          row_op(r, s, pl[q]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace cuopt_b200
 
 #include <algorithm>
 #include <cmath>
@@ -62,7 +174,8 @@ csr_host_t make_fixed(int rows, int cols, int k, uint64_t seed)
   for (int r = 0; r <= rows; ++r) A.off[r] = r * k;
 #pragma omp parallel for schedule(static)
   for (int r = 0; r < rows; ++r) {
-    uint64_t s = seed * 0x1234567ull + (uint64_t)r * 0x9e3779b97f4a7c15ull;
+    uint64_t s0 = seed * 0x632be59bd9b4e019ull + (uint64_t)r;  // decorrelate the rows: hash the row number first
+    uint64_t s  = splitmix(s0);
     int* c     = A.idx.data() + (size_t)r * k;
     for (int j = 0; j < k; ++j) c[j] = (int)(splitmix(s) % (uint64_t)cols);
     std::sort(c, c + k);
@@ -164,7 +277,7 @@ bicsr_host_t make_bicsr(const csr_host_t& A, int CH, int max_rows)
   }
   B.n_blk = (int)B.first_row.size();
   B.first_row.push_back(A.rows);
-  B.idx.assign((size_t)B.n_blk * cap, 0);
+  B.idx.assign((size_t)B.n_blk * cap, 0x7fffffff);  // padding slot: no gather at all
   B.val.assign((size_t)B.n_blk * cap, 0.0);
 #pragma omp parallel for schedule(static)
   for (int b = 0; b < B.n_blk; ++b) {
@@ -202,7 +315,7 @@ __global__ void __launch_bounds__(WARP_THREADS, RPL == 1 ? 6 : 4) k_base(csr_war
   spmv_warp_rows<payload_t, RPL>(A, x, prod[threadIdx.x >> 5], pre_op, row_op, make_l2_policies(1).keep);
 }
 
-struct bicsr_view_t {
+struct lab_bicsr_view_t {
   const int* first_row;
   const int* off;
   const int* idx;
@@ -219,7 +332,7 @@ __device__ __forceinline__ double lab_gather(const double* p, unsigned long long
 }
 
 template <int CH, int MINB, bool PREFETCH, int GATHER>
-__global__ void __launch_bounds__(256, MINB) k_bicsr(bicsr_view_t A, const double* __restrict__ x, double* __restrict__ out)
+__global__ void __launch_bounds__(256, MINB) k_bicsr(lab_bicsr_view_t A, const double* __restrict__ x, double* __restrict__ out)
 {
   __shared__ double rs_all[8][32 * CH];
   double* rsw                  = rs_all[threadIdx.x >> 5];
@@ -245,7 +358,10 @@ __global__ void __launch_bounds__(256, MINB) k_bicsr(bicsr_view_t A, const doubl
     for (int k = 0; k < CH; ++k) a[k] = ld_stream(A.val + base + k * 32);
     double g[CH];
 #pragma unroll
-    for (int k = 0; k < CH; ++k) g[k] = lab_gather<GATHER>(x + (c[k] & 0x7fffffff), pol);
+    for (int k = 0; k < CH; ++k) {
+      const int col = c[k] & 0x7fffffff;
+      g[k]          = col != 0x7fffffff ? lab_gather<GATHER>(x + col, pol) : 0.0;
+    }
     // rows of the block (first 32 of them; more only when rows are short)
     const int lo = __ldg(A.off + r0);
     int e0 = 0, e1 = 0;
@@ -260,21 +376,17 @@ __global__ void __launch_bounds__(256, MINB) k_bicsr(bicsr_view_t A, const doubl
 #pragma unroll
       for (int k = 0; k < CH; ++k) c[k] = ld_stream(A.idx + (size_t)(b + nwarps) * (32 * CH) + k * 32 + lane);
     }
-    // chunk sums, left to right; the first row end of the chunk waits for the carry of the previous lanes
+    // chunk sums, left to right (branch-free: selects and predicated stores); the first row end of the chunk waits
+    // for the carry of the previous lanes
     double s = 0.0, head = 0.0;
-    int kf = -1;
+    const int kf = ends ? __ffs(ends) - 1 : -1;
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
       s += a[k] * g[k];
-      if (ends & (1u << k)) {
-        if (kf < 0) {
-          head = s;
-          kf   = k;
-        } else {
-          rsw[k * 32 + lane] = s;
-        }
-        s = 0.0;
-      }
+      const bool e = (ends >> k) & 1u;
+      if (e && k != kf) rsw[k * 32 + lane] = s;
+      head = (k == kf) ? s : head;
+      s    = e ? 0.0 : s;
     }
     double T     = s;
     double carry = __shfl_up_sync(FULL, T, 1);
@@ -369,6 +481,13 @@ __global__ void k_flush(double* p, size_t n)
 {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 1.0;
 }
+// the same, every line tagged evict-last: what the L2 looks like in the solver, where x-bar and y' (2 x 80 MB at configs[3])
+// are stored and gathered with the "keep" policy
+__global__ void k_flush_keep(double* p, size_t n)
+{
+  const unsigned long long keep = make_l2_policies(1).keep;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) st_l2(p + i, 1.0, keep);
+}
 
 // ------------------------------------------------------------------------------------------------ harness
 template <typename T>
@@ -381,6 +500,19 @@ T* to_dev(const std::vector<T>& h, size_t slack = 64)
   return d;
 }
 
+// sequential sweep that pulls a vector into L2 (evict-last), see k_l2_warm in pdlp_kernels.cuh
+__global__ void k_warm(const double* __restrict__ x, size_t count)
+{
+  unsigned long long keep;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+  double a, b, acc = 0.0;
+  for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 2; i + 1 < count; i += (size_t)gridDim.x * blockDim.x * 2) {
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(a), "=d"(b) : "l"(x + i), "l"(keep));
+    acc += a + b;
+  }
+  if (acc == 1.2345e-300) asm volatile("trap;");
+}
+static int g_mode               = 0;  // 0 hot (back-to-back repetitions), 1 cold (L2 flushed before every repetition), 2 cold, L2 full of stale evict-last lines
 static double* g_flush   = nullptr;
 static size_t g_flush_n  = 0;
 static int g_sms         = 148;
@@ -394,7 +526,8 @@ double time_us(F launch, int reps = 9)
   cudaEventCreate(&b);
   std::vector<float> t;
   for (int i = 0; i < reps + 3; ++i) {
-    if (g_need_flush) k_flush<<<g_sms * 8, 256>>>(g_flush, g_flush_n);
+    if (g_mode == 2) k_flush_keep<<<g_sms * 8, 256>>>(g_flush, g_flush_n / 2);  // 192 MB of stale evict-last lines
+    else if (g_need_flush || g_mode) k_flush<<<g_sms * 8, 256>>>(g_flush, g_flush_n);
     cudaEventRecord(a);
     launch();
     cudaEventRecord(b);
@@ -439,19 +572,25 @@ void run_bicsr(const char* label, const csr_host_t& A, const case_dev_t& d, cons
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, k_bicsr<CH, MINB, PREFETCH, GATHER>));
   const int grid = std::max(1, std::min((B.n_blk + 7) / 8, g_sms * occ));
-  bicsr_view_t v{d_first, d.off, d_idx, d_val, B.n_blk};
+  lab_bicsr_view_t v{d_first, d.off, d_idx, d_val, B.n_blk};
   CK(cudaMemset(d.y, 0xff, (size_t)d.rows * sizeof(double)));
   k_bicsr<CH, MINB, PREFETCH, GATHER><<<grid, 256>>>(v, d.x, d.y);
   CK(cudaDeviceSynchronize());
   const double err = check(d.y, d.ref);
-  const double us  = time_us([&] { k_bicsr<CH, MINB, PREFETCH, GATHER><<<grid, 256>>>(v, d.x, d.y); });
+  double t[3];
+  for (int mode = 0; mode < 3; ++mode) {
+    g_mode = mode;
+    t[mode] = time_us([&] { k_bicsr<CH, MINB, PREFETCH, GATHER><<<grid, 256>>>(v, d.x, d.y); });
+  }
+  g_mode = 0;
+  const double us = t[0];
   const double bytes = 12.0 * d.nnz + 4.0 * (d.rows + 1) + 8.0 * (d.rows + d.cols);
-  printf("  %-34s CH=%2d occ=%d regs=%3d grid=%5d : %8.1f us  %6.1f Gnnz/s  %6.0f GB/s alg  err %.1e%s\n", label, CH, occ,
-         fa.numRegs, grid, us, d.nnz / us * 1e-3, bytes / us * 1e-3, err, err <= 1e-12 ? "" : "  WRONG");
+  printf("  %-34s CH=%2d occ=%d regs=%3d grid=%5d : hot %8.1f us  cold %8.1f  cold(keep-polluted) %8.1f  | hot %6.1f Gnnz/s %6.0f GB/s alg  err %.1e%s\n", label, CH, occ,
+         fa.numRegs, grid, us, t[1], t[2], d.nnz / us * 1e-3, bytes / us * 1e-3, err, err <= 1e-12 ? "" : "  WRONG");
   (void)A;
 }
 
-void run_case(const char* name, const csr_host_t& A, bool ceilings)
+void run_case(const char* name, const csr_host_t& A, bool ceilings, int = 0)
 {
   printf("== %s: %d x %d, nnz %zu (%.2f per row), gathered vector %.0f MB\n", name, A.rows, A.cols, A.nnz(),
          (double)A.nnz() / A.rows, A.cols * 8e-6);
@@ -492,10 +631,67 @@ void run_case(const char* name, const csr_host_t& A, bool ceilings)
     launch();
     CK(cudaDeviceSynchronize());
     const double err = check(d.y, d.ref);
-    const double us  = time_us(launch);
-    printf("  %-34s RPL=%d occ=%d grid=%5d blocks=%8d : %8.1f us  %6.1f Gnnz/s  %6.0f GB/s alg  err %.1e%s\n", "base (round-1 core)",
-           rpl, occ, grid, v.n_wb, us, d.nnz / us * 1e-3, bytes / us * 1e-3, err, err <= 1e-12 ? "" : "  WRONG");
+    double t[3];
+    for (int mode = 0; mode < 3; ++mode) {
+      g_mode  = mode;
+      t[mode] = time_us(launch);
+    }
+    g_mode          = 0;
+    const double us = t[0];
+    printf("  %-34s RPL=%d occ=%d grid=%5d blocks=%8d : hot %8.1f us  cold %8.1f  cold(keep-polluted) %8.1f  | hot %6.1f Gnnz/s %6.0f GB/s alg  err %.1e%s\n", "base (round-1 core)",
+           rpl, occ, grid, v.n_wb, us, t[1], t[2], d.nnz / us * 1e-3, bytes / us * 1e-3, err, err <= 1e-12 ? "" : "  WRONG");
     cudaFree(dwd);
+  }
+  // ---- the production kernels (pdlp_kernels.cuh) on the production format, built by the production fill kernel
+  {
+    pdhg_ctl_t hc{};
+    hc.active = 1;
+    pdhg_ctl_t* dctl;
+    CK(cudaMalloc(&dctl, sizeof(hc)));
+    CK(cudaMemcpy(dctl, &hc, sizeof(hc), cudaMemcpyHostToDevice));
+    std::vector<int2> desc;
+    for (int r = 0; r < A.rows;) {
+      const int lo = A.off[r];
+      int r1       = r;
+      while (r1 < A.rows && A.off[r1 + 1] - lo <= BICSR_SLOTS && (r1 - r) < BICSR_MAX_ROWS) ++r1;
+      if (r1 == r) { printf("long row: not in the lab\n"); exit(1); }
+      desc.push_back(make_int2(r, r1));
+      r = r1;
+    }
+    const int n_std = (int)desc.size();
+    int2* d_desc    = to_dev(desc);
+    unsigned short* d_slot;
+    int* d_bidx;
+    double* d_bval;
+    CK(cudaMalloc(&d_slot, (size_t)A.rows * 2));
+    CK(cudaMalloc(&d_bidx, (size_t)n_std * BICSR_SLOTS * 4));
+    CK(cudaMalloc(&d_bval, (size_t)n_std * BICSR_SLOTS * 8));
+    k_bicsr_fill<<<g_sms * 8, 256>>>(n_std, d_desc, d.off, d.idx, d.val, d_bidx, d_bval, d_slot);
+    CK(cudaDeviceSynchronize());
+    bicsr_view_t v{d_desc, d_slot, d_bidx, d_bval, n_std, n_std, d.off, d.idx, d.val};
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv, BICSR_THREADS, 0));
+    const int grid = std::max(1, std::min((n_std + 7) / 8, g_sms * occ));
+    CK(cudaMemset(d.y, 0xff, (size_t)d.rows * sizeof(double)));
+    k_spmv<<<grid, BICSR_THREADS>>>(v, d.x, d.y);
+    CK(cudaDeviceSynchronize());
+    const double err = check(d.y, d.ref);
+    for (int which = 0; which < 3; ++which) {
+      auto launch = [&] {
+        if (which == 0) k_spmv<<<grid, BICSR_THREADS>>>(v, d.x, d.y);
+        else k_block_pass<<<grid, BICSR_THREADS>>>(dctl, v, d.x, d.x, 0, d.y, which == 1, nullptr, 0);
+      };
+      double t[3];
+      for (int mode = 0; mode < 3; ++mode) {
+        g_mode  = mode;
+        t[mode] = time_us(launch);
+      }
+      g_mode = 0;
+      printf("  %-34s occ=%d grid=%5d blocks=%8d : hot %8.1f us  cold %8.1f  cold(keep-polluted) %8.1f  | hot %6.1f Gnnz/s %6.0f GB/s alg  err %.1e%s\n",
+             which == 0 ? "PRODUCTION k_spmv (bicsr)" : (which == 1 ? "PRODUCTION k_block_pass first=1" : "PRODUCTION k_block_pass first=0"),
+             occ, grid, n_std, t[0], t[1], t[2], d.nnz / t[0] * 1e-3, bytes / t[0] * 1e-3, err, err <= 1e-12 ? "" : "  WRONG");
+    }
+    cudaFree(d_desc); cudaFree(d_slot); cudaFree(d_bidx); cudaFree(d_bval); cudaFree(dctl);
   }
   // ---- block-interleaved CSR
   for (int CH : {8, 16}) {
@@ -505,16 +701,15 @@ void run_case(const char* name, const csr_host_t& A, bool ceilings)
     double* d_val  = to_dev(B.val);
     printf("  bicsr CH=%d: %d blocks, %.2f%% padding\n", CH, B.n_blk, 100.0 * ((double)B.n_blk * 32 * CH / A.nnz() - 1.0));
     if (CH == 8) {
-      run_bicsr<8, 4, false, 0>("bicsr", A, d, B, d_first, d_idx, d_val);
-      run_bicsr<8, 4, true, 0>("bicsr +prefetch", A, d, B, d_first, d_idx, d_val);
-      run_bicsr<8, 3, true, 0>("bicsr +prefetch minb3", A, d, B, d_first, d_idx, d_val);
-      run_bicsr<8, 6, false, 0>("bicsr minb6", A, d, B, d_first, d_idx, d_val);
-      run_bicsr<8, 5, true, 0>("bicsr +prefetch minb5", A, d, B, d_first, d_idx, d_val);
-      run_bicsr<8, 4, true, 1>("bicsr +prefetch ldg-gather", A, d, B, d_first, d_idx, d_val);
+      run_bicsr<8, 4, false, 0>("bicsr hint", A, d, B, d_first, d_idx, d_val);
+      run_bicsr<8, 4, true, 0>("bicsr hint +prefetch", A, d, B, d_first, d_idx, d_val);
+      run_bicsr<8, 4, false, 1>("bicsr ldg", A, d, B, d_first, d_idx, d_val);
+      run_bicsr<8, 4, true, 1>("bicsr ldg +prefetch", A, d, B, d_first, d_idx, d_val);
+      run_bicsr<8, 5, true, 0>("bicsr hint +prefetch minb5", A, d, B, d_first, d_idx, d_val);
+      run_bicsr<8, 6, false, 0>("bicsr hint minb6", A, d, B, d_first, d_idx, d_val);
     } else {
-      run_bicsr<16, 2, false, 0>("bicsr", A, d, B, d_first, d_idx, d_val);
-      run_bicsr<16, 2, true, 0>("bicsr +prefetch", A, d, B, d_first, d_idx, d_val);
-      run_bicsr<16, 3, false, 0>("bicsr minb3", A, d, B, d_first, d_idx, d_val);
+      run_bicsr<16, 2, true, 0>("bicsr hint +prefetch", A, d, B, d_first, d_idx, d_val);
+      run_bicsr<16, 3, false, 0>("bicsr hint minb3", A, d, B, d_first, d_idx, d_val);
     }
     cudaFree(d_first);
     cudaFree(d_idx);
@@ -567,14 +762,14 @@ int main(int argc, char** argv)
     run_case("configs[3] A, unblocked", A, true);
     {
       csr_host_t B0 = column_block(A, 0, big / 2);
-      run_case("configs[3] A, column block 0 of 2", B0, true);
+      run_case("configs[3] A, column block 0 of 2", B0, true, big / 2);
     }
     csr_host_t T = transpose(A);
     A            = csr_host_t{};
     run_case("configs[3] A^T, unblocked", T, false);
     {
       csr_host_t B0 = column_block(T, 0, big / 2);
-      run_case("configs[3] A^T, column block 0 of 2", B0, false);
+      run_case("configs[3] A^T, column block 0 of 2", B0, false, big / 2);
     }
   }
   return 0;
