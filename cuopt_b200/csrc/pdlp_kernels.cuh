@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_primal_step(const pdhg_ctl_t* __
 // (pdhg.cu:73-117 + utils.cuh:98-112) + dual half of the running average + partial ||dy||^2.
 // =============================================================================================
 // INIT: the product continues the running sum t of the earlier column blocks (gather blocking: this is the LAST block's pass)
-template <bool INIT>
-__global__ void __launch_bounds__(BICSR_THREADS, BICSR_MIN_CTAS) k_dual_step(const pdhg_ctl_t* __restrict__ ctl,
+template <bool INIT, int NPRE>
+__global__ void __launch_bounds__(BICSR_THREADS, bicsr_min_ctas(NPRE)) k_dual_step(const pdhg_ctl_t* __restrict__ ctl,
                                                                              bicsr_view_t A,
                                                                              const double* __restrict__ xbar,
                                                                              double* __restrict__ ybuf0,
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(BICSR_THREADS, BICSR_MIN_CTAS) k_dual_step(con
     const double d   = next - p.y;
     dy2 += d * d;
   };
-  spmv_bicsr_rows<payload_t, INIT>(A, xbar, rows[threadIdx.x >> 5], pre_op, row_op, pol.keep);
+  spmv_bicsr_rows<payload_t, INIT, NPRE>(A, xbar, rows[threadIdx.x >> 5], pre_op, row_op, pol.keep);
   const double tot = block_reduce(dy2, red);
   if (threadIdx.x == 0) part_dy2[blockIdx.x] = tot;
 }
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(BICSR_THREADS, BICSR_MIN_CTAS) k_dual_step(con
 // interaction = dx . (A^T y' - A^T y)  (the reference's SpMV-saving form, :267-277).
 // =============================================================================================
 // INIT: as in k_dual_step (the last column block's pass of a gather-blocked A^T y')
-template <bool INIT>
-__global__ void __launch_bounds__(BICSR_THREADS, BICSR_MIN_CTAS) k_transpose_step(pdhg_ctl_t* __restrict__ ctl,
+template <bool INIT, int NPRE>
+__global__ void __launch_bounds__(BICSR_THREADS, bicsr_min_ctas(NPRE)) k_transpose_step(pdhg_ctl_t* __restrict__ ctl,
                                                                                   bicsr_view_t AT,
                                                                                   const double* __restrict__ ybuf0,
                                                                                   const double* __restrict__ ybuf1,
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(BICSR_THREADS, BICSR_MIN_CTAS) k_transpose_ste
     acc[0] += p.dx * (s - p.aty);
     acc[1] += p.dx * p.dx;
   };
-  spmv_bicsr_rows<payload_t, INIT>(AT, yn, rows[threadIdx.x >> 5], pre_op, row_op, pol.keep);
+  spmv_bicsr_rows<payload_t, INIT, NPRE>(AT, yn, rows[threadIdx.x >> 5], pre_op, row_op, pol.keep);
 
   if (!publish_and_elect<2>(acc, parts, &ctl->ticket[0], red)) return;
   const double interaction = gather_partials(parts, gridDim.x, red);

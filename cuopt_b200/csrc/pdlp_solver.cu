@@ -246,7 +246,9 @@ struct pdlp_solver_t::impl_t {
   pdhg_ctl_t* h_ctl = nullptr;  // pinned mirrors
   eval_t* h_eval    = nullptr;
   double* h_scalar  = nullptr;
-  int occ_spmv = 1;  // resident CTAs per SM of the SpMV kernels (64 registers, 16 KB of shared memory)
+  int occ_spmv = 1;   // resident CTAs per SM of the SpMV kernels (64 registers, 16 KB of shared memory)
+  int occ_spmv2 = 1;  // ... of the fused kernels that prefetch the payload of two row groups (85 registers)
+  int npre_override = 0;  // experiment switch CUOPT_B200_SPMV_NPRE=1|2
   dvec<double> eval_m, eval_n;  // A x (current, average) and, on one GPU, A^T y (current, average)
   dvec<double> part_max;        // per_constraint_residual: per-CTA maxima, rows (2 x grid_m) then columns (2 x grid_n)
   dvec<double> part_infeas;     // infeasibility detection: rows (6 x grid_m) then columns (12 x grid_n)
@@ -320,9 +322,16 @@ struct pdlp_solver_t::impl_t {
   }
 
   // one wave of resident CTAs, or fewer when the matrix has fewer blocks than that (8 warps = 8 blocks per CTA)
-  int spmv_grid(const csr_dev_t& M) const
+  int spmv_grid(const csr_dev_t& M, int npre = 1) const
   {
-    return std::max(1, std::min((M.n_blk() + BICSR_WARPS - 1) / BICSR_WARPS, sms * occ_spmv));
+    return std::max(1, std::min((M.n_blk() + BICSR_WARPS - 1) / BICSR_WARPS, sms * (npre > 1 ? occ_spmv2 : occ_spmv)));
+  }
+  // payload row groups the fused kernels fetch ahead (spmv_bicsr.cuh): 2 when the blocks hold clearly more than 32 rows
+  int fused_npre(const csr_dev_t& M) const
+  {
+    if (npre_override) return npre_override > 1 ? 2 : 1;
+    const bicsr_dev_t& b = M.bi_structure();
+    return (b.n_std > 0 && (long long)M.rows > 40LL * b.n_std) ? 2 : 1;
   }
 
   void sync() { CUOPT_CUDA_TRY(cudaStreamSynchronize(stream)); }
@@ -404,9 +413,13 @@ struct pdlp_solver_t::impl_t {
     // carry the largest payload, so their occupancy bounds the others')
     {
       int o2 = 1, o3 = 1;
-      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, (const void*)k_dual_step<true>, BICSR_THREADS, 0));
-      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, (const void*)k_transpose_step<true>, BICSR_THREADS, 0));
+      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, (const void*)k_dual_step<true, 1>, BICSR_THREADS, 0));
+      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, (const void*)k_transpose_step<true, 1>, BICSR_THREADS, 0));
       occ_spmv = std::max(1, std::min(o2, o3));
+      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, (const void*)k_dual_step<true, 2>, BICSR_THREADS, 0));
+      CUOPT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, (const void*)k_transpose_step<true, 2>, BICSR_THREADS, 0));
+      occ_spmv2 = std::max(1, std::min(o2, o3));
+      if (const char* e = std::getenv("CUOPT_B200_SPMV_NPRE")) npre_override = std::atoi(e);
     }
     grid_k2   = spmv_grid(As);
     grid_k3   = spmv_grid(ATs);
@@ -588,7 +601,7 @@ struct pdlp_solver_t::impl_t {
     fill_bicsr_values(ATs, stream, sms);
     build_gather_blocks(As, blkA, t_m);
     build_gather_blocks(ATs, blkAT, t_n);
-    n_part_dy2 = blkA.on() ? blkA.grid[blkA.B - 1] : grid_k2;  // CTAs of the kernel that runs the dual row epilogue
+    n_part_dy2 = k2_grid();  // CTAs of the kernel that runs the dual row epilogue
     if (!hp.compute_initial_step_size_before_scaling) step = initial_step_size(As);
     if (!hp.compute_initial_primal_weight_before_scaling) weight = initial_primal_weight(cs, lcs, ucs);
 
@@ -751,33 +764,43 @@ struct pdlp_solver_t::impl_t {
   // on the last block continuing their running sum.  wait_flags: peer transport (xbar slices of the peers)
   void enqueue_k2(const unsigned long long* wait_flags, int n_wait)
   {
-    if (!blkA.on()) {
-      k_dual_step<false><<<grid_k2, BICSR_THREADS, 0, stream>>>(d_ctl.data(), As.view(), xbar.data(), ybuf[0].data(),
-                                                                ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(),
-                                                                part_dy2.data(), wait_flags, n_wait, nullptr);
-      return;
-    }
-    launch_block_passes(blkA, blkA.B - 1, xbar.data(), xbar.data(), 0, t_m.data(), wait_flags, n_wait);
-    const csr_dev_t& L = blkA.blk[blkA.B - 1];
-    k_dual_step<true><<<blkA.grid[blkA.B - 1], BICSR_THREADS, 0, stream>>>(d_ctl.data(), L.view(), xbar.data(), ybuf[0].data(),
-                                                                           ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(),
-                                                                           part_dy2.data(), nullptr, 0, t_m.data());
+    const bool blocked  = blkA.on();
+    const csr_dev_t& L  = blocked ? blkA.blk[blkA.B - 1] : As;
+    const int npre      = fused_npre(L);
+    const int grid      = spmv_grid(L, npre);
+    const double* t     = blocked ? t_m.data() : nullptr;
+    const unsigned long long* wf = blocked ? nullptr : wait_flags;
+    if (blocked) launch_block_passes(blkA, blkA.B - 1, xbar.data(), xbar.data(), 0, t_m.data(), wait_flags, n_wait);
+#define CUOPT_K2(INIT, NPRE)                                                                                             \
+  k_dual_step<INIT, NPRE><<<grid, BICSR_THREADS, 0, stream>>>(d_ctl.data(), L.view(), xbar.data(), ybuf[0].data(),       \
+                                                              ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(),      \
+                                                              part_dy2.data(), wf, n_wait, t)
+    if (blocked) { if (npre > 1) CUOPT_K2(true, 2); else CUOPT_K2(true, 1); }
+    else { if (npre > 1) CUOPT_K2(false, 2); else CUOPT_K2(false, 1); }
+#undef CUOPT_K2
+  }
+  int k2_grid() const
+  {
+    const csr_dev_t& L = blkA.on() ? blkA.blk[blkA.B - 1] : As;
+    return spmv_grid(L, fused_npre(L));
   }
   // K3 on one GPU: same structure, the step rule runs in the last CTA of the fused kernel
   void enqueue_k3()
   {
-    if (!blkAT.on()) {
-      k_transpose_step<false><<<grid_k3, BICSR_THREADS, 0, stream>>>(d_ctl.data(), ATs.view(), ybuf[0].data(), ybuf[1].data(),
-                                                                     xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
-                                                                     atybuf[1].data(), part_k3.data(), part_dy2.data(),
-                                                                     n_part_dy2, nullptr);
-      return;
-    }
-    launch_block_passes(blkAT, blkAT.B - 1, ybuf[0].data(), ybuf[1].data(), 1, t_n.data(), nullptr, 0);
-    const csr_dev_t& L = blkAT.blk[blkAT.B - 1];
-    k_transpose_step<true><<<blkAT.grid[blkAT.B - 1], BICSR_THREADS, 0, stream>>>(
-      d_ctl.data(), L.view(), ybuf[0].data(), ybuf[1].data(), xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),
-      atybuf[1].data(), part_k3.data(), part_dy2.data(), n_part_dy2, t_n.data());
+    const bool blocked = blkAT.on();
+    const csr_dev_t& L = blocked ? blkAT.blk[blkAT.B - 1] : ATs;
+    const int npre     = npre_override > 1 ? 2 : 1;  // measured at configs[3]: two payload sets pay in K2 (-20 us), not here (+19 us)
+    const int grid     = spmv_grid(L, npre);
+    const double* t    = blocked ? t_n.data() : nullptr;
+    if (blocked) launch_block_passes(blkAT, blkAT.B - 1, ybuf[0].data(), ybuf[1].data(), 1, t_n.data(), nullptr, 0);
+#define CUOPT_K3(INIT, NPRE)                                                                                              \
+  k_transpose_step<INIT, NPRE><<<grid, BICSR_THREADS, 0, stream>>>(d_ctl.data(), L.view(), ybuf[0].data(), ybuf[1].data(), \
+                                                                   xbuf[0].data(), xbuf[1].data(), atybuf[0].data(),      \
+                                                                   atybuf[1].data(), part_k3.data(), part_dy2.data(),     \
+                                                                   n_part_dy2, t)
+    if (blocked) { if (npre > 1) CUOPT_K3(true, 2); else CUOPT_K3(true, 1); }
+    else { if (npre > 1) CUOPT_K3(false, 2); else CUOPT_K3(false, 1); }
+#undef CUOPT_K3
   }
   int kernels_per_attempt() const
   {

@@ -39,6 +39,7 @@ constexpr int BICSR_WARPS           = BICSR_THREADS / 32;
 constexpr int BICSR_PAD             = 0x7fffffff;     // index of an unused slot
 constexpr unsigned short BICSR_EMPTY = 0xffff;        // row_slot of a row without entries
 constexpr int BICSR_MIN_CTAS        = 4;              // 64 registers: 8 idx + 8 next idx + 16 val + 16 gathered + payload
+__host__ __device__ constexpr int bicsr_min_ctas(int npre) { return npre > 1 ? 3 : BICSR_MIN_CTAS; }  // two payload sets: 85
 
 __host__ __device__ constexpr int bicsr_slot(int q) { return (q % BICSR_CH) * 32 + q / BICSR_CH; }
 
@@ -60,7 +61,9 @@ struct bicsr_view_t {
 // rsw: this warp's BICSR_SLOTS doubles of shared memory.
 // INIT: the row's result is P::init + (sum over this matrix's entries) — a running sum over the column blocks of a gather-
 // blocked product (pdlp_kernels.cuh).
-template <typename P, bool INIT = false, typename PreOp, typename RowOp>
+// NPRE: row groups (of 32 rows) per block whose payload is fetched ahead of the gathers: 1, or 2 for matrices with short
+// rows, whose blocks hold ~64 rows (the column blocks of a gather-blocked matrix: 4 entries per row at configs[3]).
+template <typename P, bool INIT = false, int NPRE = 1, typename PreOp, typename RowOp>
 __device__ __forceinline__ void spmv_bicsr_rows(const bicsr_view_t& A,
                                                 const double* __restrict__ x,
                                                 double* rsw,
@@ -80,12 +83,15 @@ __device__ __forceinline__ void spmv_bicsr_rows(const bicsr_view_t& A,
   for (int b = gwarp; b < A.n_std; b += nwarps) {
     const int2 d  = __ldg(A.desc + b);
     const int r0 = d.x, r1 = d.y;
-    const bool own = r0 + lane < r1;
-    P pl;
-    unsigned short slot = BICSR_EMPTY;
-    if (own) {
-      pl   = pre_op(r0 + lane);
-      slot = __ldg(A.row_slot + r0 + lane);
+    P pl[NPRE];
+    unsigned short slot[NPRE];
+#pragma unroll
+    for (int q = 0; q < NPRE; ++q) {
+      slot[q] = BICSR_EMPTY;
+      if (r0 + lane + 32 * q < r1) {
+        pl[q]   = pre_op(r0 + lane + 32 * q);
+        slot[q] = __ldg(A.row_slot + r0 + lane + 32 * q);
+      }
     }
     const size_t base = (size_t)b * BICSR_SLOTS + lane;
     double a[BICSR_CH], g[BICSR_CH];
@@ -128,12 +134,15 @@ __device__ __forceinline__ void spmv_bicsr_rows(const bicsr_view_t& A,
     }
     if (kf >= 0) rsw[kf * 32 + lane] = carry + head;
     __syncwarp();
-    if (own) {
-      double sum = slot != BICSR_EMPTY ? rsw[slot] : 0.0;
-      if constexpr (INIT) sum = pl.init + sum;
-      row_op(r0 + lane, sum, pl);
+#pragma unroll
+    for (int q = 0; q < NPRE; ++q) {
+      if (r0 + lane + 32 * q < r1) {
+        double sum = slot[q] != BICSR_EMPTY ? rsw[slot[q]] : 0.0;
+        if constexpr (INIT) sum = pl[q].init + sum;
+        row_op(r0 + lane + 32 * q, sum, pl[q]);
+      }
     }
-    for (int r = r0 + 32 + lane; r < r1; r += 32) {  // blocks of short rows hold more than 32 of them
+    for (int r = r0 + 32 * NPRE + lane; r < r1; r += 32) {  // blocks of very short rows hold more rows still
       const P p2              = pre_op(r);
       const unsigned short s2 = __ldg(A.row_slot + r);
       double sum              = s2 != BICSR_EMPTY ? rsw[s2] : 0.0;
