@@ -106,18 +106,16 @@ class ClockSampler:
 
 
 WORKLOADS = {"c4": (10_000_000, 10_000_000), "c2": (1_000_000, 1_000_000)}
-# dram__bytes_read.sum + dram__bytes_write.sum per step of the dominant kernel (group), from the ncu captures under
-# profiles/ : (workload, kernel, blocked) -> (bytes, file)
-NCU_TRAFFIC = {
-    ("c4", "k_transpose_step", True): (649.8e6 + 735.8e6 + 381.0e6, "profiles/r1/ncu_full_c4_10M_blocked.md"),
-    ("c4", "k_dual_step", True): (650.6e6 + 741.0e6 + 496.3e6, "profiles/r1/ncu_full_c4_10M_blocked.md"),
-    ("c4", "k_transpose_step", False): (4028.1e6, "profiles/r1/ncu_full_c4_10M_hints_off.md"),
-    ("c4", "k_dual_step", False): (3804.4e6, "profiles/r1/ncu_full_c4_10M_hints_off.md"),
-    ("c3", "k_transpose_step", False): (20.13e6, "profiles/r1/ncu_full_c3_pds_shaped.md"),
-    ("c3", "k_dual_step", False): (17.93e6, "profiles/r1/ncu_full_c3_pds_shaped.md"),
-    ("c2", "k_transpose_step", False): (140.4e6, "profiles/r1/ncu_full_v4_warp_sync.md"),
-    ("c2", "k_dual_step", False): (145.0e6, "profiles/r1/ncu_full_v4_warp_sync.md"),
-}
+# dram__bytes_read.sum + dram__bytes_write.sum per step of the dominant kernel (group), from the COMMITTED `ncu --set full`
+# captures under profiles/ (bench.py never runs under a profiler): (workload, kernel, blocked) -> (bytes, file).  The line
+# says `traffic_source: committed capture` so that nobody mistakes it for an in-run measurement.
+NCU_TRAFFIC = {}
+try:
+    with open(os.path.join(ROOT, "profiles", "r2", "ncu_traffic.json")) as _f:
+        for _e in json.load(_f)["entries"]:
+            NCU_TRAFFIC[(_e["workload"], _e["kernel"], bool(_e["blocked"]))] = (_e["bytes_per_step"], _e["source"])
+except Exception:  # noqa: BLE001
+    pass
 TRANSPORTS = {"p2p": "NVLink peer stores issued by the producing kernels (xbar slices, A_g^T y partials, 3 scalars); "
                      "no NCCL inside the PDHG loop",
               "nccl": "NCCL all-gather(xbar) + reduce-scatter(A_g^T y) + all-reduce(3 scalars) per attempt",
@@ -147,6 +145,80 @@ def config_dict(args, lp, n_gpus):
                          % (lp.algorithmic_bytes_per_iteration() / 1e6)}
 
 
+def time_cpu_oracle(lp, cores, iterations, repeats):
+    """ONE protocol for both CPU numbers of this file (cpu_baseline of the GPU arm, the --impl reference arm): the oracle
+    port with `cores` OpenMP threads, initialised, then 12 untimed iterations — the first 10 PDLP iterations are each a
+    major iteration (termination evaluation + restart test, pdlp.cu:1082-1090), which is not the steady state the metric
+    is about — then `repeats` timed samples of `iterations` iterations.  Returns (iterations/s, seconds per sample)."""
+    from oracle import pdlp_oracle as po
+    o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=0.0,
+                  num_threads=cores)
+    o.initialise()
+    o.run(12)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        o.run(iterations)
+    dt = time.perf_counter() - t0
+    return repeats * iterations / dt, dt / repeats
+
+
+def reference_dual_simplex_leg(lp, cap_seconds):
+    """the reference's OWN CPU path for an LP is its dual simplex (single-threaded, dual_simplex/solve.hpp:64-67),
+    compiled unchanged into oracle/_ref.  On the 1M / 10M workloads it is not expected to finish: it runs in a child process
+    under `cap_seconds` and the outcome — optimal with its time, or DNF — is reported, never omitted."""
+    import multiprocessing as mp
+
+    def child(q):
+        try:
+            from oracle import ref_cpu
+            if not ref_cpu.available():
+                q.put({"status": "unavailable", "why": "oracle/_ref/libcuopt_ref_cpu.so not built on this box"})
+                return
+            r = ref_cpu.dual_simplex(lp.offsets, lp.indices, lp.values, lp.con_lb, lp.con_ub, lp.c, lp.var_lb, lp.var_ub,
+                                     time_limit=float(cap_seconds))
+            q.put({"status": r["status"], "objective": r["objective"], "iterations": r["iterations"], "seconds": r["seconds"]})
+        except Exception as e:  # noqa: BLE001
+            q.put({"status": "error", "why": str(e)[:200]})
+
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    pr = ctx.Process(target=child, args=(q,))
+    t0 = time.perf_counter()
+    pr.start()
+    pr.join(cap_seconds + 60.0)
+    out = {"status": "DNF", "why": f"no answer {cap_seconds + 60:.0f} s after the start (cap {cap_seconds:.0f} s)"}
+    if pr.is_alive():
+        pr.kill()
+        pr.join()
+    elif not q.empty():
+        out = q.get()
+        if out.get("status") in ("TIME_LIMIT", "ITERATION_LIMIT"):
+            out["status"] = "DNF (" + out["status"] + ")"
+    out["wall_seconds"] = time.perf_counter() - t0
+    out["cap_seconds"] = cap_seconds
+    out["cores"] = 1
+    out["what"] = "reference dual simplex (cpp/src/dual_simplex compiled unchanged, oracle/_ref), the LP of this bench line"
+    return out
+
+
+def cusparse_comparator(lp, timeout_s=240):
+    """The "kernel to beat" (BASELINE.md §4): the reference's PDHG attempt re-assembled from cusparseSpMV(CSR_ALG2) on A and
+    A^T, element-wise kernels, cublasDdot and a CUDA graph per attempt (scripts/cusparse_pdhg.cu), on a uniformly random
+    matrix of this LP's shape, timed on this GPU in a child process.  None when the binary is absent or the LP is not one
+    of the square sparse workloads."""
+    exe = os.path.join(ROOT, "scripts", "_bin", "cusparse_pdhg")
+    if not os.path.exists(exe) or lp.m != lp.n or lp.nnz != 8 * lp.m:
+        return None
+    try:
+        r = subprocess.run([exe, str(lp.m)], capture_output=True, text=True, timeout=timeout_s)
+        for line in r.stdout.splitlines():
+            if line.startswith("{"):
+                return json.loads(line)
+    except Exception as e:  # noqa: BLE001
+        return {"comparator": "cusparse_pdhg", "error": str(e)[:200]}
+    return None
+
+
 def run_reference(args):
     """CPU arm: the reference's PDLP as restated by the oracle port, all host threads, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -154,21 +226,12 @@ def run_reference(args):
         return
     cores = usable_cores()
     os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun presets 1; must be set before the OpenMP runtime starts
-    from oracle import pdlp_oracle as po
     lp = workload(args)
-    o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=0.0,
-                  num_threads=cores)
-    o.initialise()
     sample = args.cpu_iters
-    for _ in range(args.warmup):
-        o.run(5)
-    t0 = time.perf_counter()
-    done = 0
-    for _ in range(args.steps):
-        o.run(sample)
-        done += sample
-    dt = time.perf_counter() - t0
-    v = done / dt
+    for _ in range(max(0, args.warmup - 1)):
+        pass  # the warm-up of this arm is the untimed initialisation + 12 iterations of time_cpu_oracle
+    v, per = time_cpu_oracle(lp, cores, sample, args.steps)
+    dt = per * args.steps
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -193,9 +256,14 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=0,
                     help="oracle iterations per step (CPU arm / cpu_baseline); 0 = sized to ~20 s from the nnz count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gap-iteration-limit", type=int, default=8000,
+    ap.add_argument("--gap-iteration-limit", type=int, default=400000,
                     help="iteration cap of the untimed time-to-1e-6-gap solve reported in detail (0 = skip)")
+    ap.add_argument("--gap-time-limit", type=float, default=150.0, help="time cap (s) of that solve")
     ap.add_argument("--profile-reps", type=int, default=200)
+    ap.add_argument("--simplex-cap", type=float, default=40.0,
+                    help="seconds given to the reference's own CPU path (dual simplex, 1 core) on this LP; 0 = skip")
+    ap.add_argument("--comparator", default="auto", choices=["auto", "off"],
+                    help="time the cuSPARSE/cuBLAS re-assembly of the reference's attempt (scripts/cusparse_pdhg.cu) beside ours")
     args = ap.parse_args()
     if args.cpu_iters <= 0:  # the OpenMP oracle runs roughly 1e8 nonzeros/s of PDHG iteration on 8 cores
         nnz_guess = {"c4": 80e6, "c2": 8e6, "c3": 0.9e6}[args.workload]
@@ -227,6 +295,8 @@ def main():
         from cuopt_b200 import dist as cdist
         comm = cdist.bootstrap(rank, world, device=torch.device("cuda", local))
 
+    gsol_status = [None]
+
     def one_step():
         # e2e path: HOST numpy buffers -> C ABI -> HOST result buffers
         if world == 1:
@@ -240,6 +310,7 @@ def main():
             raise RuntimeError(sol.error_string)
         x = sol.primal(); y = sol.dual()
         st = sol.stats()
+        gsol_status[0] = sol.termination_reason
         return st, float(x[0] + y[0])
 
     def barrier():
@@ -279,7 +350,8 @@ def main():
     # the same call as the timed steps, outside the timed region; collective at N > 1
     to_gap = None
     if args.gap_iteration_limit > 0:
-        gs = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False, iteration_limit=args.gap_iteration_limit)
+        gs = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False, iteration_limit=args.gap_iteration_limit,
+                           time_limit=args.gap_time_limit)
         gs.set("optimality_tolerance", 1e-6)
         saved, settings = settings, gs
         barrier()
@@ -291,7 +363,10 @@ def main():
         to_gap = {"tolerance": 1e-6, "wall_seconds": tg, "solver_loop_seconds": gst.pdhg_loop_seconds + gst.termination_seconds,
                   "iterations": gst.number_of_steps_taken, "relative_gap": gst.relative_gap,
                   "primal_objective": gst.primal_objective, "planted_optimum": lp.optimal_objective,
-                  "reached": bool(gst.relative_gap <= 1e-6 and gst.number_of_steps_taken < args.gap_iteration_limit)}
+                  "dual_objective": gst.dual_objective,
+                  "relative_primal_residual": gst.l2_relative_primal_residual,
+                  "relative_dual_residual": gst.l2_relative_dual_residual, "status": gsol_status[0],
+                  "reached": bool(gsol_status[0] == "Optimal")}
 
     # roofline of the dominant kernel, measured in situ with CUDA events on the solver's stream
     roof = None
@@ -309,13 +384,16 @@ def main():
         achieved = by / (ms * 1e-3) / 1e9
         blocks = {"k_dual_step": prof.blocks_dual, "k_transpose_step": prof.blocks_transpose}.get(dom, 1)
         launched_as = dom if blocks <= 1 else (
-            f"{blocks} x k_block_pass + " + ("k_dual_epilogue" if dom == "k_dual_step" else "k_transpose_epilogue")
-            + " (gather blocking: the step's fused kernel split by column blocks, timed as one group)")
+            f"{blocks - 1} x k_block_pass + {dom}<INIT> on the last column block (gather blocking: the step's product is split "
+            "by column blocks, the row epilogue is fused into the last block's pass; timed as one group)")
         # DRAM traffic of that step from the committed `ncu --set full` capture of the same workload (bytes per step)
         traffic, traffic_src = NCU_TRAFFIC.get((args.workload, dom, blocks > 1), (None, None))
         roof = {"bound": "hbm", "kernel": dom, "launched_as": launched_as, "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_kind, "algorithmic_bytes_per_launch": by, "ms_per_launch": ms}
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                "traffic_source": None if traffic is None else f"committed capture: {traffic_src}",
+                "peak_source": peak_kind, "algorithmic_bytes_per_launch": by, "ms_per_launch": ms,
+                "measured_on": "1 GPU, the full LP" + ("" if world == 1 else
+                               f" (a probe on rank 0's GPU beside the {world}-GPU run: the sharded attempt runs other kernels on 1/{world} of the rows; see detail.kernels)")}
         b_iter = lp.algorithmic_bytes_per_iteration()
         extra = {"kernels": {k: {"ms": v[0], "algorithmic_GBps": v[1] / (v[0] * 1e-3) / 1e9} for k, v in ks.items()},
                  "iteration": {"ms_in_batch": prof.ms_iteration, "algorithmic_bytes": b_iter,
@@ -323,6 +401,13 @@ def main():
                                "frac_of_hbm_peak": b_iter / (prof.ms_iteration * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                  "grids": {"primal": prof.grid_primal, "dual": prof.grid_dual, "transpose": prof.grid_transpose},
                  "setup_seconds_per_step": setup_s / args.steps, "time_to_gap": to_gap}
+        if args.comparator == "auto" and world == 1:
+            comp = cusparse_comparator(lp)
+            if comp is not None:
+                if "us_attempt_graph" in comp:
+                    comp["ours_us_attempt_in_batch"] = 1e3 * prof.ms_iteration
+                    comp["ours_vs_comparator"] = comp["us_attempt_graph"] / (1e3 * prof.ms_iteration)
+                extra["cusparse_comparator"] = comp
     if rank == 0 and args.workload == "c3":
         # the reference's own CPU path on this LP (dual simplex, 1 core), from the committed fixture — not re-timed here
         try:
@@ -336,13 +421,12 @@ def main():
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
             cores = usable_cores()
             os.environ["OMP_NUM_THREADS"] = str(cores)
-            from oracle import pdlp_oracle as po
-            o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=0.0,
-                          num_threads=cores)
-            o.initialise(); o.run(5)
-            tc = time.perf_counter(); o.run(args.cpu_iters * 3); tc = time.perf_counter() - tc
-            cpu = {"value": args.cpu_iters * 3 / tc, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{args.cpu_iters * 3} PDLP iterations of the same LP by oracle/pdlp_oracle.cpp (OpenMP)"}
+            v_cpu, _ = time_cpu_oracle(lp, cores, args.cpu_iters, 3)
+            cpu = {"value": v_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"3 x {args.cpu_iters} PDLP iterations of the same LP by oracle/pdlp_oracle.cpp (OpenMP), after "
+                             "12 untimed iterations (same protocol as --impl reference)"}
+        if args.simplex_cap > 0 and world == 1:
+            extra["reference_cpu_path"] = reference_dual_simplex_leg(lp, args.simplex_cap)
 
     if rank == 0:
         h2d = 12 * lp.nnz + 4 * (lp.m + 1) + 8 * (3 * lp.n + 2 * lp.m)  # A once (A^T is built on the device) + c,l,u,lc,uc

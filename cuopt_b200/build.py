@@ -63,5 +63,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+CLI = os.path.join(HERE, "bin", "cuopt_cli")
+
+
+def build_cli(force: bool = False) -> str:
+    """cuopt_b200/bin/cuopt_cli: the command-line runner over the C ABI (csrc/cuopt_cli.cpp), linked against lib/libcuopt.so."""
+    lib = build()
+    src = os.path.join(CSRC, "cuopt_cli.cpp")
+    if not force and os.path.exists(CLI) and os.path.getmtime(CLI) >= max(os.path.getmtime(src), os.path.getmtime(lib)):
+        return CLI
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cmd = [nvcc_path(), "-O2", "-std=c++17", "-x", "cu", "-gencode", "arch=compute_100a,code=sm_100a",
+           "-I" + os.path.join(ROOT, "include"), src, "-o", CLI, "-L" + LIB_DIR, "-lcuopt",
+           "-Xlinker", "-rpath,$ORIGIN/../lib", "-Xcompiler", "-pthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed (cuopt_cli)")
+    return CLI
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_cli(force="--force" in sys.argv))

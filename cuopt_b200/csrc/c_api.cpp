@@ -7,6 +7,8 @@
 #include "pdlp_solver.hpp"
 #include "solver_settings.hpp"
 
+#include <cuda_runtime.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -32,10 +34,49 @@ struct solver_handle_t {
   bool finished = false;
 };
 
-template <typename T>
-void copy_out(T* dst, const std::vector<T>& src)
+// The reference's C layer moves every array with raft::copy, which takes host or device pointers on either side
+// (cuopt_c.cpp:110-135 for the inputs, :261-266 for the getters).  Same here: a pointer the CUDA runtime knows as device or
+// managed memory is copied with cudaMemcpy, anything else (also: no driver on this host) is plain host memory.
+bool is_device_pointer(const void* p)
 {
-  if (!src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(T));
+  if (p == nullptr) return false;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+template <typename T, typename A>
+void copy_out(T* dst, const std::vector<T, A>& src)
+{
+  if (src.empty()) return;
+  if (is_device_pointer(dst)) {  // getters have no error channel beyond their status: a failed copy leaves dst untouched
+    if (cudaMemcpy(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) cudaGetLastError();
+    return;
+  }
+  std::memcpy(dst, src.data(), src.size() * sizeof(T));
+}
+template <typename T>
+void copy_in(hvec<T>& dst, const T* src, size_t n)
+{
+  if (n > 0 && is_device_pointer(src)) {
+    dst.resize(n);
+    if (cudaMemcpy(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost) != cudaSuccess)
+      throw lp_error(error_type_t::RuntimeError, "copy from a device buffer failed");
+    return;
+  }
+  parallel_assign(dst, src, n);
+}
+void copy_in(std::vector<char>& dst, const char* src, size_t n)
+{
+  dst.resize(n);
+  if (n > 0 && is_device_pointer(src)) {
+    if (cudaMemcpy(dst.data(), src, n, cudaMemcpyDeviceToHost) != cudaSuccess)
+      throw lp_error(error_type_t::RuntimeError, "copy from a device buffer failed");
+    return;
+  }
+  if (n > 0) std::memcpy(dst.data(), src, n);
 }
 
 cuopt_int_t fill_problem_common(lp_problem_t& p,
@@ -56,16 +97,16 @@ cuopt_int_t fill_problem_common(lp_problem_t& p,
   p.n_variables      = n;
   p.maximize         = (sense == CUOPT_MAXIMIZE);
   p.objective_offset = offset;
-  p.objective_coefficients.assign(c, c + n);
-  const cuopt_int_t nnz = off[m];
+  copy_in(p.objective_coefficients, c, (size_t)n);
+  copy_in(p.A_offsets, off, (size_t)m + 1);
+  const cuopt_int_t nnz = p.A_offsets[m];
   if (nnz < 0) return CUOPT_INVALID_ARGUMENT;
-  p.A_offsets.assign(off, off + m + 1);
-  p.A_indices.assign(idx, idx + nnz);
-  p.A_values.assign(val, val + nnz);
-  p.variable_lower_bounds.assign(lb, lb + n);
-  p.variable_upper_bounds.assign(ub, ub + n);
-  p.variable_types.resize(n);
-  for (int j = 0; j < n; ++j) p.variable_types[j] = types[j] == CUOPT_CONTINUOUS ? 'C' : 'I';  // cuopt_c.cpp:127-131
+  copy_in(p.A_indices, idx, (size_t)nnz);
+  copy_in(p.A_values, val, (size_t)nnz);
+  copy_in(p.variable_lower_bounds, lb, (size_t)n);
+  copy_in(p.variable_upper_bounds, ub, (size_t)n);
+  copy_in(p.variable_types, types, (size_t)n);
+  for (int j = 0; j < n; ++j) p.variable_types[j] = p.variable_types[j] == CUOPT_CONTINUOUS ? 'C' : 'I';  // cuopt_c.cpp:127-131
   return CUOPT_SUCCESS;
 }
 
@@ -164,8 +205,8 @@ cuopt_int_t cuOptCreateProblem(cuopt_int_t num_constraints,
                                       constraint_matrix_column_indices, constraint_matrix_coefficent_values, lower_bounds,
                                       upper_bounds, variable_types))
       return rc;
-    p->row_types.assign(constraint_sense, constraint_sense + num_constraints);
-    p->constraint_bounds.assign(rhs, rhs + num_constraints);
+    copy_in(p->row_types, constraint_sense, (size_t)num_constraints);
+    copy_in(p->constraint_bounds, rhs, (size_t)num_constraints);
     *problem_ptr = p.release();
   } catch (const std::exception&) {
     return CUOPT_INVALID_ARGUMENT;
@@ -200,8 +241,8 @@ cuopt_int_t cuOptCreateRangedProblem(cuopt_int_t num_constraints,
                                       constraint_matrix_column_indices, constraint_matrix_coefficients,
                                       variable_lower_bounds, variable_upper_bounds, variable_types))
       return rc;
-    p->constraint_lower_bounds.assign(constraint_lower_bounds, constraint_lower_bounds + num_constraints);
-    p->constraint_upper_bounds.assign(constraint_upper_bounds, constraint_upper_bounds + num_constraints);
+    copy_in(p->constraint_lower_bounds, constraint_lower_bounds, (size_t)num_constraints);
+    copy_in(p->constraint_upper_bounds, constraint_upper_bounds, (size_t)num_constraints);
     *problem_ptr = p.release();
   } catch (const std::exception&) {
     return CUOPT_INVALID_ARGUMENT;

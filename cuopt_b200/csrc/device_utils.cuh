@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -24,6 +25,23 @@ namespace cuopt_b200 {
           std::to_string(__LINE__));                                                                      \
     }                                                                                                     \
   } while (0)
+
+// CUOPT_B200_TRACE=1: time spent inside cudaMalloc / cudaFree (reported by the solver when it is destroyed)
+struct alloc_stats_t {
+  bool on = false;
+  double malloc_s = 0.0, free_s = 0.0;
+  long n_malloc = 0, n_free = 0;
+  size_t bytes = 0;
+};
+inline alloc_stats_t& alloc_stats()
+{
+  static alloc_stats_t s;
+  return s;
+}
+inline double alloc_clock()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // Device array with value semantics disabled; memory comes straight from cudaMalloc
 // (one allocation per vector, sized once per solve: no pool needed at 180 GB HBM).
@@ -49,13 +67,28 @@ class dvec {
     n_     = n;
     slack_ = slack;
     if (n + slack) {
+      alloc_stats_t& as = alloc_stats();
+      const double t0   = as.on ? alloc_clock() : 0.0;
       CUOPT_CUDA_TRY(cudaMalloc(&p_, (n + slack) * sizeof(T)));
+      if (as.on) {
+        as.malloc_s += alloc_clock() - t0;
+        as.n_malloc += 1;
+        as.bytes += (n + slack) * sizeof(T);
+      }
       if (slack) CUOPT_CUDA_TRY(cudaMemset(p_ + n, 0, slack * sizeof(T)));
     }
   }
   void release()
   {
-    if (p_) cudaFree(p_);
+    if (p_) {
+      alloc_stats_t& as = alloc_stats();
+      const double t0   = as.on ? alloc_clock() : 0.0;
+      cudaFree(p_);
+      if (as.on) {
+        as.free_s += alloc_clock() - t0;
+        as.n_free += 1;
+      }
+    }
     p_ = nullptr;
     n_ = 0;
   }

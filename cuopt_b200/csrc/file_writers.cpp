@@ -29,7 +29,7 @@ bool write_problem_as_mps(const lp_problem_t& p, const std::string& path)
   if (!f.is_open()) return false;
   const double inf = std::numeric_limits<double>::infinity();
   const int m = p.n_constraints, n = p.n_variables;
-  std::vector<double> lc, uc, lb, ub;
+  hvec<double> lc, uc, lb, ub;
   p.row_bounds(lc, uc);
   p.variable_bounds(lb, ub);
   // column-major copy of A (the reference walks its transposed CSR)

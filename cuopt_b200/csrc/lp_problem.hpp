@@ -13,6 +13,10 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <atomic>
+#include <algorithm>
+#include <cstring>
+#include <thread>
 
 namespace cuopt_b200 {
 
@@ -32,6 +36,54 @@ struct lp_error : public std::runtime_error {
   error_type_t type;
 };
 
+// Host-side helpers for 10M-row problems: the C ABI copies every array it is given (cuopt_c.cpp:115-135) and validates
+// the CSR; single-threaded that is ~0.4 s of a 1.4 GB problem, so both run on a few worker threads.
+template <typename F>
+inline void parallel_chunks(size_t n, F&& body, size_t min_chunk = size_t(1) << 20)
+{
+  const size_t hw   = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+  const size_t n_th = std::max<size_t>(1, std::min(hw, n / min_chunk));
+  if (n_th <= 1) {
+    body(size_t(0), n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t per = (n + n_th - 1) / n_th;
+  for (size_t t = 0; t < n_th; ++t) {
+    const size_t lo = t * per, hi = std::min(n, lo + per);
+    if (lo >= hi) break;
+    pool.emplace_back([&body, lo, hi]() { body(lo, hi); });
+  }
+  for (auto& th : pool) th.join();
+}
+// Vector whose resize() leaves trivially constructible elements uninitialised: a 640 MB array is then first touched by
+// the worker threads that fill it, not zeroed by one thread first.
+template <typename T>
+struct noinit_allocator : std::allocator<T> {
+  template <typename U>
+  struct rebind {
+    using other = noinit_allocator<U>;
+  };
+  template <typename U, typename... Args>
+  void construct(U* p, Args&&... args)
+  {
+    if constexpr (sizeof...(Args) == 0) ::new (static_cast<void*>(p)) U;
+    else ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+  }
+};
+template <typename T>
+using hvec = std::vector<T, noinit_allocator<T>>;
+
+template <typename T>
+inline void parallel_assign(hvec<T>& dst, const T* src, size_t n)
+{
+  dst.resize(n);
+  if (n == 0) return;
+  T* d = dst.data();
+  parallel_chunks(n, [d, src](size_t lo, size_t hi) { std::memcpy(d + lo, src + lo, (hi - lo) * sizeof(T)); },
+                  (size_t(4) << 20) / sizeof(T));
+}
+
 struct lp_problem_t {
   int n_constraints = 0;
   int n_variables   = 0;
@@ -40,21 +92,21 @@ struct lp_problem_t {
   double objective_scaling_factor = 1.0;
 
   // CSR constraint matrix A (n_constraints x n_variables)
-  std::vector<int> A_offsets{0};
-  std::vector<int> A_indices;
-  std::vector<double> A_values;
+  hvec<int> A_offsets{0};
+  hvec<int> A_indices;
+  hvec<double> A_values;
 
-  std::vector<double> objective_coefficients;  // c
-  std::vector<double> variable_lower_bounds;   // may be empty -> 0
-  std::vector<double> variable_upper_bounds;   // may be empty -> +inf
+  hvec<double> objective_coefficients;  // c
+  hvec<double> variable_lower_bounds;   // may be empty -> 0
+  hvec<double> variable_upper_bounds;   // may be empty -> +inf
   std::vector<char> variable_types;            // 'C' / 'I', may be empty -> all continuous
 
   // "sense" form (cuOptCreateProblem, MPS): row type 'E'/'G'/'L' + right-hand side
   std::vector<char> row_types;
-  std::vector<double> constraint_bounds;  // b
+  hvec<double> constraint_bounds;  // b
   // "ranged" form (cuOptCreateRangedProblem, MPS after RANGES): lc <= A x <= uc
-  std::vector<double> constraint_lower_bounds;
-  std::vector<double> constraint_upper_bounds;
+  hvec<double> constraint_lower_bounds;
+  hvec<double> constraint_upper_bounds;
 
   std::string problem_name, objective_name;
   std::vector<std::string> variable_names, row_names;
@@ -81,9 +133,17 @@ struct lp_problem_t {
     for (size_t i = 1; i < A_offsets.size(); ++i)
       if (A_offsets[i] < A_offsets[i - 1]) fail("A_offsets values must in an increasing order.");
     if ((size_t)A_offsets.back() != A_values.size()) fail("A_offsets last value must equal the number of nonzeros.");
-    for (int j : A_indices)
-      if (j < 0 || j >= n_variables)
-        fail("A_indices values must positive lower than the number of variables (c size).");
+    {
+      std::atomic<bool> bad{false};
+      const int* idx = A_indices.data();
+      const int nv   = n_variables;
+      parallel_chunks(A_indices.size(), [&bad, idx, nv](size_t lo, size_t hi) {
+        bool b = false;
+        for (size_t p = lo; p < hi; ++p) b |= (idx[p] < 0) | (idx[p] >= nv);
+        if (b) bad = true;
+      });
+      if (bad) fail("A_indices values must positive lower than the number of variables (c size).");
+    }
     if (constraint_lower_bounds.empty() != constraint_upper_bounds.empty())
       fail("Constraints lower bounds must be set along with constraints upper bounds.");
     const bool have_ranged = !constraint_lower_bounds.empty();
@@ -114,7 +174,7 @@ struct lp_problem_t {
   // Two-sided row bounds as PDLP uses them.  Rule of the reference's problem_t
   // construction (cpp/src/mip/problem/problem_helpers.cuh:34-87): explicit lower/upper
   // bounds win; otherwise E -> [b,b], G -> [b,+inf], L -> [-inf,b].
-  void row_bounds(std::vector<double>& lo, std::vector<double>& hi) const
+  void row_bounds(hvec<double>& lo, hvec<double>& hi) const
   {
     const double inf = std::numeric_limits<double>::infinity();
     if (!constraint_lower_bounds.empty()) {
@@ -136,7 +196,7 @@ struct lp_problem_t {
   }
 
   // Default variable bounds [0, +inf) when not given (problem_helpers.cuh:89-116).
-  void variable_bounds(std::vector<double>& lo, std::vector<double>& hi) const
+  void variable_bounds(hvec<double>& lo, hvec<double>& hi) const
   {
     lo = variable_lower_bounds;
     hi = variable_upper_bounds;

@@ -476,7 +476,7 @@ struct reader_t {
       out.A_values.insert(out.A_values.end(), row_vals[i].begin(), row_vals[i].end());
       out.A_offsets.push_back((int)out.A_indices.size());
     }
-    out.constraint_bounds = rhs;
+    out.constraint_bounds.assign(rhs.begin(), rhs.end());
     out.constraint_lower_bounds.resize(m);
     out.constraint_upper_bounds.resize(m);
     for (size_t i = 0; i < m; ++i) {

@@ -1200,6 +1200,19 @@ __global__ void k_fill(int n, double* __restrict__ v, double value)
   const int stride = gridDim.x * blockDim.x;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) v[j] = value;
 }
+__global__ void k_scale_constant(int n, double* __restrict__ v, double a)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) v[j] *= a;
+}
+// *count += number of positions with lo > hi (problem validation on the device: the arrays are uploaded unchecked)
+__global__ void k_count_crossed_bounds(int n, const double* __restrict__ lo, const double* __restrict__ hi, int* __restrict__ count)
+{
+  const int stride = gridDim.x * blockDim.x;
+  int bad          = 0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) bad += lo[j] > hi[j];
+  if (bad) atomicAdd(count, bad);
+}
 __global__ void k_clamp(int n, double* __restrict__ v, const double* __restrict__ lo, const double* __restrict__ hi)
 {
   const int stride = gridDim.x * blockDim.x;

@@ -19,6 +19,7 @@
 #include "trust_region.cuh"
 
 #include <math_constants.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <chrono>
@@ -27,6 +28,7 @@
 #include <cstdlib>
 #include <atomic>
 #include <map>
+#include <mutex>
 #include <thread>
 #include <string>
 
@@ -103,7 +105,8 @@ std::vector<T> cut_in_segments(int rows, F cut_segment)
 
 // Cuts the rows into BICSR blocks (whole consecutive rows, <= 256 entries, <= 256 rows; a longer row is a long-row block)
 // from HOST row offsets, uploads the descriptors and fills the interleaved arrays on the device from d's plain CSR.
-void build_bicsr(csr_dev_t& d, const std::vector<int>& off, cudaStream_t s, int sms)
+template <typename VI>
+void build_bicsr(csr_dev_t& d, const VI& off, cudaStream_t s, int sms)
 {
   const int all_rows = (int)off.size() - 1;
   constexpr int LONG = (int)0x80000000u;
@@ -155,17 +158,8 @@ void fill_bicsr_values(csr_dev_t& d, cudaStream_t s, int sms)
   }
 }
 
-void upload_csr(csr_dev_t& d, int rows, int cols, const std::vector<int>& off, const std::vector<int>& idx,
-                const std::vector<double>& val, cudaStream_t s, int sms)
-{
-  d.rows = rows;
-  d.cols = cols;
-  d.nnz  = (int)val.size();
-  d.off.upload(off, s);
-  d.idx.upload(idx, s);
-  d.val.upload(val, s);
-  build_bicsr(d, off, s, sms);
-}
+template <typename VI, typename VD>
+void upload_csr(csr_dev_t& d, int rows, int cols, const VI& off, const VI& idx, const VD& val, cudaStream_t s, int sms);
 
 }  // namespace
 
@@ -204,6 +198,116 @@ int ew_grid(int n, int sms) { return std::max(1, std::min((n + EW_THREADS - 1) /
 double now_seconds()
 {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// NVTX phase ranges (nsys / ncu timelines), named like the reference's raft::common::nvtx::range scopes where a phase is
+// the same (pdlp.cu:541 "Check termination", pdlp_restart_strategy.cu:288 "run trust region restart", :656
+// "compute_restart", convergence_information.cu:158 "compute_convergence_information", ...).  Header-only NVTX3: no cost
+// without a profiler attached.
+struct nvtx_range_t {
+  explicit nvtx_range_t(const char* name) { nvtxRangePushA(name); }
+  ~nvtx_range_t() { nvtxRangePop(); }
+  nvtx_range_t(const nvtx_range_t&)            = delete;
+  nvtx_range_t& operator=(const nvtx_range_t&) = delete;
+};
+
+// CUOPT_B200_TRACE=1: wall-clock of the setup phases on stderr (each mark synchronises the stream first)
+struct phase_trace_t {
+  bool on = false;
+  double t = 0.0;
+  cudaStream_t stream = nullptr;
+  void start(cudaStream_t s)
+  {
+    const char* e = std::getenv("CUOPT_B200_TRACE");
+    on            = e != nullptr && e[0] == '1';
+    alloc_stats().on = on;
+    stream        = s;
+    t             = now_seconds();
+  }
+  void mark(const char* what)
+  {
+    if (!on) return;
+    if (stream) cudaStreamSynchronize(stream);
+    const double now = now_seconds();
+    std::fprintf(stderr, "[cuopt-b200 trace] %-44s %8.1f ms\n", what, 1e3 * (now - t));
+    t = now;
+  }
+};
+
+// Host -> device copies of the problem arrays go through a process-wide ring of pinned staging buffers: worker threads copy
+// the caller's pageable memory into a slot while the DMA engine drains the previous ones (a plain cudaMemcpy from pageable
+// memory does the same internally, single-threaded, at ~10 GB/s; this reaches the PCIe rate).  One ring per device, allocated
+// on first use and kept: page-locking 128 MB costs more than one upload.
+class staged_uploader_t {
+ public:
+  static staged_uploader_t& get()  // one ring per device: its events belong to the device that was current at creation
+  {
+    static staged_uploader_t per_device[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return per_device[dev & 63];
+  }
+  void upload(void* dst, const void* src, size_t bytes, cudaStream_t s)
+  {
+    if (bytes == 0) return;
+    std::lock_guard<std::mutex> guard(mu_);
+    if (!ensure() || bytes < SLOT / 4) {  // small arrays, or no pinned memory to be had: the plain path
+      CUOPT_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+      return;
+    }
+    const char* from = static_cast<const char*>(src);
+    char* to         = static_cast<char*>(dst);
+    for (size_t done = 0; done < bytes;) {
+      const int k    = next_;
+      next_          = (next_ + 1) % SLOTS;
+      const size_t b = std::min(SLOT, bytes - done);
+      CUOPT_CUDA_TRY(cudaEventSynchronize(free_[k]));  // the DMA that last read this slot has finished
+      char* slot = buf_ + (size_t)k * SLOT;
+      parallel_chunks(b, [slot, from, done](size_t lo, size_t hi) { std::memcpy(slot + lo, from + done + lo, hi - lo); },
+                      size_t(2) << 20);
+      CUOPT_CUDA_TRY(cudaMemcpyAsync(to + done, slot, b, cudaMemcpyHostToDevice, s));
+      CUOPT_CUDA_TRY(cudaEventRecord(free_[k], s));
+      done += b;
+    }
+  }
+
+ private:
+  static constexpr size_t SLOT = size_t(32) << 20;
+  static constexpr int SLOTS   = 4;
+  std::mutex mu_;
+  char* buf_ = nullptr;
+  bool tried_ = false;
+  int next_ = 0;
+  cudaEvent_t free_[SLOTS] = {};
+  bool ensure()
+  {
+    if (tried_) return buf_ != nullptr;
+    tried_ = true;
+    if (cudaMallocHost(&buf_, SLOT * SLOTS) != cudaSuccess) {
+      cudaGetLastError();
+      buf_ = nullptr;
+      return false;
+    }
+    for (auto& e : free_) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return true;
+  }
+};
+template <typename T, typename V>
+void upload_staged(dvec<T>& d, const V& h, cudaStream_t s)
+{
+  d.resize(h.size());
+  staged_uploader_t::get().upload(d.data(), h.data(), h.size() * sizeof(T), s);
+}
+template <typename VI, typename VD>
+void upload_csr(csr_dev_t& d, int rows, int cols, const VI& off, const VI& idx, const VD& val, cudaStream_t s, int sms)
+{
+  d.rows = rows;
+  d.cols = cols;
+  d.nnz  = (int)val.size();
+  upload_staged(d.off, off, s);
+  upload_staged(d.idx, idx, s);
+  upload_staged(d.val, val, s);
+  build_bicsr(d, off, s, sms);
 }
 
 }  // namespace
@@ -311,6 +415,11 @@ struct pdlp_solver_t::impl_t {
 
   ~impl_t()
   {
+    if (trace.on) {
+      const alloc_stats_t& a = alloc_stats();
+      std::fprintf(stderr, "[cuopt-b200 trace] so far in this process: %ld cudaMalloc %.1f ms (%.2f GB), %ld cudaFree %.1f ms\n",
+                   a.n_malloc, 1e3 * a.malloc_s, a.bytes * 1e-9, a.n_free, 1e3 * a.free_s);
+    }
     close_peer_memory(false);
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
     if (ev_a) cudaEventDestroy(ev_a);
@@ -338,9 +447,13 @@ struct pdlp_solver_t::impl_t {
   void check_launch() { CUOPT_CUDA_TRY(cudaGetLastError()); }
 
   // ------------------------------------------------------------------------------- construction
+  phase_trace_t trace;
   void build(const lp_problem_t& p, const pdlp_settings_t& settings)
   {
+    nvtx_range_t nvtx_scope("pdlp build: upload, transpose, block-interleaved matrices");
+    trace.start(nullptr);
     p.check_representation();
+    trace.mark("check_representation");
     st       = settings;
     hp       = pdlp_hyper_params_t::preset(settings.pdlp_solver_mode);
     m        = p.n_constraints;
@@ -366,27 +479,59 @@ struct pdlp_solver_t::impl_t {
       CUOPT_CUDA_TRY(cudaMemcpyToSymbol(g_l2_hints, &on, sizeof(int)));
     }
 
-    // problem_t construction semantics (mip/problem/problem.cu:55-93, problem_helpers.cuh:34-142)
-    std::vector<double> hc = p.objective_coefficients, hl, hu, hlc, huc;
-    p.variable_bounds(hl, hu);
-    p.row_bounds(hlc, huc);
+    // problem_t construction semantics (mip/problem/problem.cu:55-93, problem_helpers.cuh:34-142): maximise => c <- -c,
+    // default variable bounds [0, +inf), row senses -> two-sided bounds.  The caller's arrays go to the device as they are
+    // (no host copies); negation, defaults and the bound checks run there.
     obj_scale  = p.objective_scaling_factor;
     obj_offset = p.objective_offset;
-    if (maximize) {
-      for (auto& v : hc) v = -v;
-      obj_scale = -obj_scale;
-    }
-    for (int j = 0; j < n; ++j)
-      if (hl[j] > hu[j]) throw lp_error(error_type_t::ValidationError, "Variable lower bound above upper bound");
-    for (int i = 0; i < m; ++i)
-      if (hlc[i] > huc[i]) throw lp_error(error_type_t::ValidationError, "Constraint lower bound above upper bound");
-
+    if (maximize) obj_scale = -obj_scale;
+    trace.stream = stream;
+    trace.mark("stream + pinned control buffers");
     upload_csr(A, m, n, p.A_offsets, p.A_indices, p.A_values, stream, sms);
+    trace.mark("upload A + BICSR(A)");
     transpose_to(AT, A, stream, sms);
+    trace.mark("transpose + BICSR(A^T)");
     As.alias_structure_copy_values(A, stream);
     ATs.alias_structure_copy_values(AT, stream);
-    c.upload(hc, stream); l.upload(hl, stream); u.upload(hu, stream); lc.upload(hlc, stream); uc.upload(huc, stream);
+    const int gn = ew_grid(n, sms), gm = ew_grid(m, sms);
+    upload_staged(c, p.objective_coefficients, stream);
+    if (maximize) k_scale_constant<<<gn, EW_THREADS, 0, stream>>>(n, c.data(), -1.0);
+    if (p.variable_lower_bounds.empty()) {
+      l.resize(n);
+      k_fill<<<gn, EW_THREADS, 0, stream>>>(n, l.data(), 0.0);
+    } else {
+      upload_staged(l, p.variable_lower_bounds, stream);
+    }
+    if (p.variable_upper_bounds.empty()) {
+      u.resize(n);
+      k_fill<<<gn, EW_THREADS, 0, stream>>>(n, u.data(), std::numeric_limits<double>::infinity());
+    } else {
+      upload_staged(u, p.variable_upper_bounds, stream);
+    }
+    if (!p.constraint_lower_bounds.empty()) {
+      upload_staged(lc, p.constraint_lower_bounds, stream);
+      upload_staged(uc, p.constraint_upper_bounds, stream);
+    } else {
+      hvec<double> hlc, huc;
+      p.row_bounds(hlc, huc);
+      upload_staged(lc, hlc, stream);
+      upload_staged(uc, huc, stream);
+      sync();  // hlc / huc go out of scope
+    }
+    {
+      dvec<int> bad(2);
+      bad.zero(stream);
+      k_count_crossed_bounds<<<gn, EW_THREADS, 0, stream>>>(n, l.data(), u.data(), bad.data());
+      k_count_crossed_bounds<<<gm, EW_THREADS, 0, stream>>>(m, lc.data(), uc.data(), bad.data() + 1);
+      check_launch();
+      int h_bad[2] = {0, 0};
+      CUOPT_CUDA_TRY(cudaMemcpyAsync(h_bad, bad.data(), sizeof(h_bad), cudaMemcpyDeviceToHost, stream));
+      sync();
+      if (h_bad[0]) throw lp_error(error_type_t::ValidationError, "Variable lower bound above upper bound");
+      if (h_bad[1]) throw lp_error(error_type_t::ValidationError, "Constraint lower bound above upper bound");
+    }
     cs.copy_from(c, stream); ls.copy_from(l, stream); us.copy_from(u, stream); lcs.copy_from(lc, stream); ucs.copy_from(uc, stream);
+    trace.mark("objective / bound vectors");
 
     // sharded: primal vectors that travel by all-gather are padded to world * nslice (the pad is never read as data)
     size_t pad = 0;
@@ -466,6 +611,7 @@ struct pdlp_solver_t::impl_t {
     d_eval.resize(2);
     d_eval.zero(stream);
     sync();
+    trace.mark("vectors, grids, work buffers");
   }
 
   // sharded solve: pick the transport of the PDHG attempt and set up its buffers (collective)
@@ -532,6 +678,7 @@ struct pdlp_solver_t::impl_t {
   // initial_scaling.cu:85-307
   void compute_scaling_vectors()
   {
+    nvtx_range_t nvtx_scope("compute_scaling_vectors (Ruiz + Pock-Chambolle)");
     k_fill<<<grid_m, EW_THREADS, 0, stream>>>(m, Dr.data(), 1.0);
     k_fill<<<grid_n, EW_THREADS, 0, stream>>>(n, Dc.data(), 1.0);
     const int wg_m = std::max(1, std::min((m + 7) / 8, sms * 16));
@@ -560,6 +707,7 @@ struct pdlp_solver_t::impl_t {
   // initial_scaling.cu:348-408
   void scale_problem()
   {
+    nvtx_range_t nvtx_scope("scale_problem");
     const int wg_m = std::max(1, std::min((m + 7) / 8, sms * 16));
     const int wg_n = std::max(1, std::min((n + 7) / 8, sms * 16));
     k_scale_matrix<<<wg_m, 256, 0, stream>>>(m, As.off_ptr(), As.idx_ptr(), As.val.data(), Dr.data(), Dc.data());
@@ -588,19 +736,25 @@ struct pdlp_solver_t::impl_t {
   void initialise()
   {
     if (initialised) return;
+    nvtx_range_t nvtx_scope("pdlp initialise: scaling, initial step size / primal weight");
     const double t0 = now_seconds();
     // norms of the unscaled problem used by the relative tolerances (convergence_information.cu:74-82)
+    trace.mark("(gap between build and initialise)");
     l2_norm_c = std::sqrt(setup_reduce(1, n, c.data(), nullptr, 1.0));
     l2_norm_b = std::sqrt(setup_reduce(2, m, lc.data(), uc.data(), 1.0, true));
+    trace.mark("norms");
     compute_scaling_vectors();
+    trace.mark("scaling vectors (Ruiz + Pock-Chambolle)");
     double step = 0.0, weight = 0.0;
     if (hp.compute_initial_step_size_before_scaling) step = initial_step_size(A);
     if (hp.compute_initial_primal_weight_before_scaling) weight = initial_primal_weight(c, lc, uc);
     scale_problem();
     fill_bicsr_values(As, stream, sms);
     fill_bicsr_values(ATs, stream, sms);
+    trace.mark("scale problem + scaled BICSR values");
     build_gather_blocks(As, blkA, t_m);
     build_gather_blocks(ATs, blkAT, t_n);
+    trace.mark("gather blocks");
     n_part_dy2 = k2_grid();  // CTAs of the kernel that runs the dual row epilogue
     if (!hp.compute_initial_step_size_before_scaling) step = initial_step_size(As);
     if (!hp.compute_initial_primal_weight_before_scaling) weight = initial_primal_weight(cs, lcs, ucs);
@@ -623,6 +777,7 @@ struct pdlp_solver_t::impl_t {
     }
     check_launch();
     sync();
+    trace.mark("initial step size / primal weight, control block");
     sol.stats.initial_step_size     = step;
     sol.stats.initial_primal_weight = weight;
     sol.stats.setup_seconds += now_seconds() - t0;
@@ -918,6 +1073,7 @@ struct pdlp_solver_t::impl_t {
   void run_steps(int steps)
   {
     if (steps <= 0) return;
+    nvtx_range_t nvtx_scope("take_step batch (PDHG attempts up to the next major iteration)");
     CUOPT_CUDA_TRY(cudaEventRecord(ev_a, stream));
     if (need_aty) {  // pdhg.cu:183-202
       const int cur = h_ctl->parity;
@@ -983,6 +1139,7 @@ struct pdlp_solver_t::impl_t {
   // averages, in-place unscaling, evaluation of current and average (pdlp.cu:1103-1142 up to check_termination's inputs)
   void evaluate_iterates()
   {
+    nvtx_range_t nvtx_scope("compute_convergence_information (current + average)");
     const int cur  = h_ctl->parity;
     // pdlp.cu:1100-1129: warm start given and no step taken yet => the averages handed in are used as they are
     const int mode = (warm_started && h_ctl->accepted == 0) ? 2 : (h_ctl->accepted <= 1) ? 0 : 1;
@@ -1176,8 +1333,9 @@ struct pdlp_solver_t::impl_t {
     return false;
   }
 
-  bool check_termination()  // pdlp.cu:538-802 (first_primal_feasible handled, infeasibility detection not implemented)
+  bool check_termination()  // pdlp.cu:538-802
   {
+    nvtx_range_t nvtx_scope("Check termination");
     if (total_pdlp_iterations <= 1) return check_limits();
     const int sc = h_eval[0].status, sa = h_eval[1].status;
     if (st.first_primal_feasible) {  // :587-633
@@ -1243,6 +1401,7 @@ struct pdlp_solver_t::impl_t {
   }
   void tr_bound(tr_gap_t& g)  // bound_optimal_objective, :1034-1051
   {
+    nvtx_range_t nvtx_scope("bound_optimal_objective");
     const int N = n + m;
     launch_spmv(ATs, g.py, tr_aty.data());
     launch_spmv(As, g.px, tr_ax.data());
@@ -1273,6 +1432,7 @@ struct pdlp_solver_t::impl_t {
   }
   void trust_region_restart()  // pdlp_restart_strategy.cu:278-364
   {
+    nvtx_range_t nvtx_scope("run trust region restart");
     if (h_ctl->its_since_restart == 0) return;
     const int cur = h_ctl->parity;
     bool restart  = should_do_artificial_restart(total_pdlp_iterations);
@@ -1330,6 +1490,7 @@ struct pdlp_solver_t::impl_t {
 
   void kkt_restart()  // pdlp_restart_strategy.cu:468-641
   {
+    nvtx_range_t nvtx_scope("compute_restart");
     const int cur        = h_ctl->parity;
     const double kkt_cur = h_eval[0].kkt;
     if (h_ctl->its_since_restart == 0) {

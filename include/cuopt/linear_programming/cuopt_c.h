@@ -19,8 +19,9 @@
  *     which also nulls the caller's handle
  *   - functions return CUOPT_SUCCESS or one of the CUOPT_* error codes; no
  *     C++ exception crosses this boundary
- *   - pointers are HOST pointers (the reference additionally accepts device
- *     pointers through raft::copy)
+ *   - array pointers may be HOST or DEVICE / managed pointers on either side
+ *     (inputs of the Create calls, destinations of the getters), like the
+ *     reference's raft::copy-based C layer (cuopt_c.cpp:110-135, :261-266)
  */
 #ifndef CUOPT_C_API_H
 #define CUOPT_C_API_H

@@ -16,7 +16,7 @@
 // captured in one CUDA graph per attempt like the reference does; the per-attempt host synchronisation the reference
 // needs is reported separately (with and without).
 //
-// nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fopenmp scripts/cusparse_pdhg.cu -lcusparse -lcublas -o gpurun_out/cusparse_pdhg
+// nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fopenmp scripts/cusparse_pdhg.cu -lcusparse -lcublas -o scripts/_bin/cusparse_pdhg   (python -c "import __graft_entry__ as g; g.build_tools()")
 #include <cublas_v2.h>
 #include <cuda_runtime.h>
 #include <cusparse.h>

@@ -109,6 +109,26 @@ def test_two_gpu_solve_matches_single_gpu(mode, transport):
     assert res[0]["rp"] <= 1e-6 * (1.0 + np.linalg.norm(np.where(np.isfinite(lp.con_ub), lp.con_ub, lp.con_lb))) * 10
 
 
+@pytest.mark.parametrize("world", [4, 8])
+def test_four_and_eight_gpu_solve_matches_single_gpu(world):
+    """The same comparison on 4 and 8 ranks (peer-store transport; slices of 1/4 and 1/8 of the columns, rank-ordered sums of
+    4 / 8 partials): run with gpurun --gpus 4 / 8, skipped on smaller boxes."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    size, tol = 40_000, 1e-6
+    res = _solve_on_gpus(world, size, tol, 1, "p2p")
+    lp, one = _single_gpu(size, tol, 1)
+    st1 = one.stats()
+    assert res[0]["status"] == 1
+    assert res[0]["obj"] == pytest.approx(lp.optimal_objective, rel=1e-5)
+    assert res[0]["obj"] == pytest.approx(st1.primal_objective, rel=1e-5)
+    assert res[0]["dobj"] == pytest.approx(st1.dual_objective, rel=1e-5)
+    assert abs(res[0]["its"] - st1.number_of_steps_taken) <= max(40, 0.4 * st1.number_of_steps_taken)
+    y = np.concatenate([r["y"] for r in res])
+    assert y.shape[0] == lp.m and all(r["rows"][1] - r["rows"][0] == len(r["y"]) for r in res)
+
+
 def test_peer_store_transport_is_deterministic_and_equals_nccl_transport():
     """With two ranks a + b == b + a, so the peer-store transport (rank-ordered sums) and the NCCL transport must
     produce bit-identical iterates; and the peer-store transport must reproduce itself run to run (no race between the

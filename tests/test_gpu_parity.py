@@ -312,22 +312,22 @@ def test_blocked_kernels_follow_the_oracle_step_by_step(forced_blocks, mode):
 
 
 def test_blocked_and_fused_paths_solve_identically(forced_blocks, monkeypatch):
+    """Fused kernels vs gather-blocked passes (+ fused last pass) on the same LP, solved to 1e-8: the same optimum to 1e-6 in
+    the objective (round-1 finding: at tolerance 1e-6 two such runs are 1e-4 apart, which says nothing; at 1e-8 the bound
+    holds).  Iteration counts still react to last-bit differences through the restart decisions."""
     for lp in (lpgen.sparse_lp(3000, 2500, 6, seed=11), lpgen.multicommodity(60, 200, 4, seed=2)):
         p = lp_problem(lp)
         s = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False)
-        s.set("optimality_tolerance", 1e-6)
+        s.set("optimality_tolerance", 1e-8)
         monkeypatch.delenv("CUOPT_B200_GATHER_BLOCK_BYTES", raising=False)
         fused = capi.solve(p, s)
         forced_blocks(8 * lp.n / 2.5)
         blocked = capi.solve(p, s)
         assert fused.termination_status == blocked.termination_status == 1
-        # the row sums are the same (entry order kept, running sum continued); the norm reductions have another shape,
-        # so the two runs are equal to rounding, not to the bit
         fs, bs = fused.stats(), blocked.stats()
-        # (iteration counts at 1e-6 react to last-bit differences through the restart decisions: 2120 vs 1720 measured)
         assert abs(bs.number_of_steps_taken - fs.number_of_steps_taken) <= max(40, 0.4 * fs.number_of_steps_taken)
-        # two different tolerance-1e-6 points (residuals of 1e-6 (1 + ||b||) move the objective by more than the gap)
-        assert bs.primal_objective == pytest.approx(fs.primal_objective, rel=1e-4, abs=1e-9)
+        assert bs.primal_objective == pytest.approx(fs.primal_objective, rel=OBJECTIVE, abs=1e-9)
+        assert bs.dual_objective == pytest.approx(fs.dual_objective, rel=OBJECTIVE, abs=1e-9)
         assert np.linalg.norm(blocked.primal() - fused.primal()) <= 1e-3 * max(1.0, np.linalg.norm(fused.primal()))
 
 

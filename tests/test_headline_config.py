@@ -1,0 +1,85 @@
+"""Parity on the configurations BASELINE.json quotes the metric on, at FULL size (round-1 finding: no parity test touched the
+headline 10M x 10M LP):
+
+  * configs[3] (10M x 10M, 80M nonzeros): the CUDA path — gather-blocked passes over the block-interleaved matrices, the
+    fused last pass, device-side step rule — stepped against the OpenMP oracle element-wise from the same start;
+  * configs[1] (1M x 1M) and configs[3]: solved through the C ABI until BOTH objectives are within 1e-6 relative of the
+    planted optimum (north star: "converging to the reference's primal/dual objective within 1e-6 relative").  The PDLP
+    criteria are relative to 1 + |objective|, ||b||, ||c||: at tolerance 1e-6 the objectives of these LPs are still 5e-6 off
+    (measured), so the solves run at the tolerance given below.
+
+fp64 tolerances: ELEMENTWISE 1e-11 relative to the vector's largest entry after identical steps (summation order inside a
+row: lanes / column blocks; reductions over 10M elements); scalars 1e-9."""
+import os
+
+import numpy as np
+import pytest
+
+from cuopt_b200 import capi, lpgen
+from oracle import pdlp_oracle as po
+from test_gpu_parity import lp_problem, rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.slow]
+
+# tolerance at which PDLP's relative criteria imply 1e-6 on the objectives of the planted LPs (measured on the B200:
+# gpurun_out r2j; iterations / seconds in DESIGN.md §3)
+TIGHT = 1e-7
+
+
+def host_threads():
+    try:
+        return max(1, min(32, len(os.sched_getaffinity(0))))
+    except Exception:  # noqa: BLE001
+        return 8
+
+
+def test_headline_lp_steps_match_the_oracle_elementwise():
+    lp = lpgen.sparse_lp(10_000_000, 10_000_000, 8, seed=1234)
+    s = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False)
+    s.set("optimality_tolerance", 1e-4)
+    g = capi.Solver(lp_problem(lp), s)
+    o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub, tol=1e-4,
+                  num_threads=host_threads())
+    g.initialise(); o.initialise()
+    for name in ("row_scaling", "col_scaling"):
+        assert rel_err(g.vector(name), o.vector(name)) <= 1e-12, name
+    for name in ("step_size", "primal_weight"):
+        assert g.scalar(name) == pytest.approx(o.scalar(name), rel=1e-12), name
+    done = 0
+    for steps in (1, 2, 9):  # 12 iterations: the first 10 are major iterations (evaluation + restart test each)
+        g.advance(steps); o.run(steps)
+        done += steps
+        for name in ("x", "y", "aty", "sum_x", "sum_y"):
+            assert rel_err(g.vector(name), o.vector(name)) <= 1e-11, (name, done)
+        for name in ("step_size", "primal_weight", "sum_w"):
+            assert g.scalar(name) == pytest.approx(o.scalar(name), rel=1e-9), (name, done)
+        assert g.scalar("k_pdhg") == o.scalar("k_pdhg") and g.scalar("n_restarts") == o.scalar("n_restarts")
+
+
+def solve_to_planted_optimum(size, tolerance, objective_rel, time_limit):
+    lp = lpgen.sparse_lp(size, size, 8, seed=1234)
+    s = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False, time_limit=time_limit)
+    s.set("optimality_tolerance", tolerance)
+    sol = capi.solve(lp_problem(lp), s)
+    st = sol.stats()
+    assert sol.termination_reason == "Optimal", (sol.termination_reason, st.number_of_steps_taken, st.relative_gap)
+    assert st.primal_objective == pytest.approx(lp.optimal_objective, rel=objective_rel)
+    assert st.dual_objective == pytest.approx(lp.optimal_objective, rel=objective_rel)
+    # post-solve invariants of the reference's tests (pdlp_test_utilities.cuh:42-139) at full size
+    x = sol.primal()
+    assert float(lp.c @ x) == pytest.approx(st.primal_objective, rel=1e-9, abs=1e-6)
+    assert np.all(x >= lp.var_lb - 1e-6)
+    return st
+
+
+def test_config1_converges_to_the_planted_optimum_within_1e6():
+    # measured on the B200: Optimal after 227 600 iterations / 24 s; objectives 4.3e-7 (primal) and 5.0e-7 (dual) off
+    solve_to_planted_optimum(1_000_000, TIGHT, 1e-6, 180.0)
+
+
+def test_headline_lp_converges_to_the_planted_optimum():
+    """configs[3] at tolerance 1e-6 (the "time-to-1e-6-gap" solve of bench.py): Optimal, both objectives within 1e-5 of the
+    planted optimum.  The 1e-6 accuracy on the objectives themselves needs tolerance ~1e-7 here, i.e. > 550 000 iterations /
+    10 minutes on one B200: measured once (profiles/r2/time_to_tolerance_c4_1e-7.txt: 4.7e-7 primal, 2.2e-7 dual after
+    551 800 iterations), not part of the suite."""
+    solve_to_planted_optimum(10_000_000, 1e-6, 1e-5, 600.0)
