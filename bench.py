@@ -116,7 +116,10 @@ try:
             NCU_TRAFFIC[(_e["workload"], _e["kernel"], bool(_e["blocked"]))] = (_e["bytes_per_step"], _e["source"])
 except Exception:  # noqa: BLE001
     pass
-TRANSPORTS = {"p2p": "NVLink peer stores issued by the producing kernels (xbar slices, A_g^T y partials, 3 scalars); "
+TRANSPORTS = {"gather": "every rank owns 1/N of the rows of A and 1/N of the rows of A^T; xbar and y' are all-gathered by NVLink "
+                        "peer stores issued by the kernels that produce them (K1, K2), 3 scalars per rank; no partial "
+                        "products, no NCCL inside the PDHG loop",
+              "p2p": "NVLink peer stores issued by the producing kernels (xbar slices, A_g^T y partials, 3 scalars); "
                      "no NCCL inside the PDHG loop",
               "nccl": "NCCL all-gather(xbar) + reduce-scatter(A_g^T y) + all-reduce(3 scalars) per attempt",
               "allreduce": "primal side replicated, one NCCL all-reduce of n+1 doubles per attempt"}
@@ -135,7 +138,7 @@ def workload(args):
 def config_dict(args, lp, n_gpus):
     names = {"c4": "configs[3] instance (the 10M-var LP the metric is quoted on)", "c2": "configs[1]",
              "c3": "configs[2] (pds-shaped multicommodity flow, synthesised: no pds file in the tree)"}
-    transport = os.environ.get("CUOPT_B200_DIST_MODE", "p2p")
+    transport = os.environ.get("CUOPT_B200_DIST_MODE", "gather")
     return {"workload": f"{names[args.workload]}: {lp.name}, {lp.m}x{lp.n}, nnz {lp.nnz}, fp64",
             "rows": lp.m, "cols": lp.n, "nnz": lp.nnz, "iterations_per_step": args.iters,
             "pdlp_solver_mode": "Stable2",
@@ -291,9 +294,12 @@ def main():
     settings.set("optimality_tolerance", 0.0)  # never stop early: every step runs exactly `iters` iterations
 
     comm = None
+    shard = None
     if world > 1:
         from cuopt_b200 import dist as cdist
         comm = cdist.bootstrap(rank, world, device=torch.device("cuda", local))
+        shard = cdist.shard_rows(lp, rank, world)
+        shard = shard[:2] + tuple(np.ascontiguousarray(a) for a in shard[2:])
 
     gsol_status = [None]
 
@@ -303,8 +309,9 @@ def main():
             p = capi.Problem.create_ranged(lp.offsets, lp.indices, lp.values, lp.con_lb, lp.con_ub, lp.c, lp.var_lb,
                                            lp.var_ub)
             sol = capi.solve(p, settings)
-        else:  # this rank's block of constraint rows; collective solve
-            p, _ = cdist.local_problem(lp, rank, world)
+        else:  # this rank's block of constraint rows (host arrays cut once, outside the timed region); collective solve
+            _, _, off, idx, val, clb, cub = shard
+            p = capi.Problem.create_ranged(off, idx, val, clb, cub, lp.c, lp.var_lb, lp.var_ub)
             sol = capi.solve_distributed(p, settings, comm)
         if sol.return_code != 0:
             raise RuntimeError(sol.error_string)
@@ -417,7 +424,7 @@ def main():
             pass
     if rank == 0:
         extra["solver_seconds_per_step"] = {"pdhg_batches": loop_s / args.steps, "major_iterations": term_s / args.steps}
-        extra["transport"] = os.environ.get("CUOPT_B200_DIST_MODE", "p2p") if world > 1 else None
+        extra["transport"] = os.environ.get("CUOPT_B200_DIST_MODE", "gather") if world > 1 else None
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
             cores = usable_cores()
             os.environ["OMP_NUM_THREADS"] = str(cores)

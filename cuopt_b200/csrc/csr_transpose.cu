@@ -153,6 +153,17 @@ void sort_keys_with_index(int count, const double* keys_in, double* keys_out, co
   CUOPT_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.data(), bytes, keys_in, keys_out, vals_in, vals_out, count, 0, 64, stream));
   CUOPT_CUDA_TRY(cudaStreamSynchronize(stream));
 }
+void exclusive_sum_int(int count, const int* in, int* out, cudaStream_t stream)
+{
+  if (count <= 0) return;
+  size_t bytes = 0;
+  CUOPT_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, count, stream));
+  dvec<unsigned char> tmp(bytes + 16);
+  bytes = tmp.size();
+  CUOPT_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.data(), bytes, in, out, count, stream));
+  CUOPT_CUDA_TRY(cudaStreamSynchronize(stream));  // tmp goes out of scope
+}
+
 void inclusive_sum_in_place(int count, double* values, cudaStream_t stream)
 {
   size_t bytes = 0;

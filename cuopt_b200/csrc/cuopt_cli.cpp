@@ -103,6 +103,12 @@ bool parse(int argc, char** argv, options_t& o)
         auto it = modes.find(v);
         if (it != modes.end()) v = it->second;
       }
+      if (name == "optimality_tolerance") {  // run_pdlp.cu:52-55, :104: set_optimality_tolerance = all six tolerances
+        for (const char* t : {CUOPT_ABSOLUTE_DUAL_TOLERANCE, CUOPT_RELATIVE_DUAL_TOLERANCE, CUOPT_ABSOLUTE_PRIMAL_TOLERANCE,
+                              CUOPT_RELATIVE_PRIMAL_TOLERANCE, CUOPT_ABSOLUTE_GAP_TOLERANCE, CUOPT_RELATIVE_GAP_TOLERANCE})
+          o.params.emplace_back(t, v);
+        continue;
+      }
       o.params.emplace_back(name, v);
     }
   }

@@ -240,8 +240,10 @@ __global__ void __launch_bounds__(EW_THREADS) k_primal_step(const pdhg_ctl_t* __
 // (pdhg.cu:73-117 + utils.cuh:98-112) + dual half of the running average + partial ||dy||^2.
 // =============================================================================================
 // INIT: the product continues the running sum t of the earlier column blocks (gather blocking: this is the LAST block's pass)
-template <bool INIT, int NPRE>
-__global__ void __launch_bounds__(BICSR_THREADS, bicsr_min_ctas(NPRE)) k_dual_step(const pdhg_ctl_t* __restrict__ ctl,
+// BCAST (multi-GPU "gather" transport): y' of this rank's rows also goes to the packed y' buffer of every rank that reads
+// the row (peer stores over NVLink, y_peers.p[r] = rank r's buffer) and the last CTA raises the y' flag.
+template <bool INIT, int NPRE, bool BCAST = false>
+__global__ void __launch_bounds__(BICSR_THREADS, bicsr_min_ctas(NPRE)) k_dual_step(pdhg_ctl_t* __restrict__ ctl,
                                                                              bicsr_view_t A,
                                                                              const double* __restrict__ xbar,
                                                                              double* __restrict__ ybuf0,
@@ -252,11 +254,18 @@ __global__ void __launch_bounds__(BICSR_THREADS, bicsr_min_ctas(NPRE)) k_dual_st
                                                                              double* __restrict__ part_dy2,
                                                                              const unsigned long long* xbar_flags,
                                                                              int n_xbar_flags,
-                                                                             const double* __restrict__ t)
+                                                                             const double* __restrict__ t,
+                                                                             peer_ptrs_t y_peers = peer_ptrs_t{},
+                                                                             peer_flags_t flags = peer_flags_t{},
+                                                                             int world = 1,
+                                                                             int rank = 0,
+                                                                             const int* __restrict__ send = nullptr,
+                                                                             int send_stride = 0)
 {
   if (!ctl->active) return;
   __shared__ double rows[BICSR_WARPS][BICSR_SLOTS];
   __shared__ double red[32];
+  const unsigned long long epoch = (unsigned long long)ctl->attempts + 1ull;
   // multi-GPU peer transport: xbar slices arrive by NVLink stores of the other ranks' K1s (see k_primal_step_bcast)
   if (xbar_flags) peer_wait(xbar_flags, n_xbar_flags, (unsigned long long)ctl->attempts + 1ull);
   const int cur      = ctl->parity;
@@ -286,12 +295,21 @@ __global__ void __launch_bounds__(BICSR_THREADS, bicsr_min_ctas(NPRE)) k_dual_st
     const double up  = next + sigma * p.uc;
     next             = fmax(low, fmin(up, 0.0));
     st_l2(yn + i, next, pol.keep);  // K3 gathers from y': keep it in L2
+    if constexpr (BCAST) {  // send[r * send_stride + i]: where row i lives in rank r's packed y' (-1: rank r never reads it)
+#pragma unroll
+      for (int r = 0; r < DIST_MAX_PEERS; ++r)
+        if (r < world) {
+          const int d = __ldg(send + (size_t)r * send_stride + i);
+          if (d >= 0) y_peers.p[r][d] = next;
+        }
+    }
     const double d   = next - p.y;
     dy2 += d * d;
   };
   spmv_bicsr_rows<payload_t, INIT, NPRE>(A, xbar, rows[threadIdx.x >> 5], pre_op, row_op, pol.keep);
   const double tot = block_reduce(dy2, red);
   if (threadIdx.x == 0) part_dy2[blockIdx.x] = tot;
+  if constexpr (BCAST) peer_signal_grid_done(&ctl->ticket[2], flags, world, DIST_FLAG_PARTIAL + rank, epoch);
 }
 
 // =============================================================================================
@@ -349,6 +367,146 @@ __global__ void __launch_bounds__(BICSR_THREADS, bicsr_min_ctas(NPRE)) k_transpo
   if (threadIdx.x != 0) return;
 
   pdhg_step_rule(ctl, interaction, dx2, dy2);
+}
+
+// Multi-GPU "gather" transport: rank g also owns ROWS J_g OF THE GLOBAL A^T (n_g x m, all constraint rows as columns), so
+// A^T y' on its slice is a complete row sum over the all-gathered y' (yfull: every rank's K2 stores its rows there) —
+// no partial products, no reduce-scatter, and per rank exactly 1/G of the single-GPU K3.  Row j is LOCAL to the slice
+// (the x / A^T y pointers are offset by the slice start).  Tail: {interaction, ||dx||^2 of the slice, ||dy||^2 of this
+// rank's rows} go to the scalar table of every rank (as in k_interaction_slice); k_step_rule_gather follows.
+template <bool INIT, int NPRE>
+__global__ void __launch_bounds__(BICSR_THREADS, bicsr_min_ctas(NPRE)) k_transpose_step_slice(pdhg_ctl_t* __restrict__ ctl,
+                                                                                        bicsr_view_t AT,
+                                                                                        const double* __restrict__ yfull,
+                                                                                        const double* __restrict__ xbuf0,
+                                                                                        const double* __restrict__ xbuf1,
+                                                                                        double* __restrict__ aty0,
+                                                                                        double* __restrict__ aty1,
+                                                                                        double* __restrict__ parts,
+                                                                                        const double* __restrict__ part_dy2,
+                                                                                        int n_part_dy2,
+                                                                                        const double* __restrict__ t,
+                                                                                        const unsigned long long* wait_flags,
+                                                                                        int n_wait,
+                                                                                        peer_ptrs_t scal_peers,
+                                                                                        peer_flags_t flags,
+                                                                                        int world,
+                                                                                        int rank)
+{
+  if (!ctl->active) return;
+  __shared__ double rows[BICSR_WARPS][BICSR_SLOTS];
+  __shared__ double red[32];
+  const unsigned long long epoch = (unsigned long long)ctl->attempts + 1ull;
+  if (wait_flags) peer_wait(wait_flags, n_wait, epoch);
+  const int cur     = ctl->parity;
+  const double* x   = cur ? xbuf1 : xbuf0;
+  const double* xn  = cur ? xbuf0 : xbuf1;
+  const double* aty = cur ? aty1 : aty0;
+  double* atyn      = cur ? aty0 : aty1;
+  double acc[2]     = {0.0, 0.0};  // interaction, ||dx||^2
+  const l2_policy_t pol = make_l2_policies(g_l2_hints);
+  struct payload_t {
+    double dx, aty, init;
+  };
+  auto pre_op = [&](int j) {
+    payload_t p;
+    p.dx   = ld_l2(xn + j, pol.stream) - ld_l2(x + j, pol.stream);
+    p.aty  = ld_l2(aty + j, pol.stream);
+    p.init = INIT ? ld_l2(t + j, pol.stream) : 0.0;
+    return p;
+  };
+  auto row_op = [&](int j, double s, const payload_t& p) {
+    st_l2(atyn + j, s, pol.stream);
+    acc[0] += p.dx * (s - p.aty);
+    acc[1] += p.dx * p.dx;
+  };
+  spmv_bicsr_rows<payload_t, INIT, NPRE>(AT, yfull, rows[threadIdx.x >> 5], pre_op, row_op, pol.keep);
+
+  if (!publish_and_elect<2>(acc, parts, &ctl->ticket[0], red)) return;
+  const double interaction = gather_partials(parts, gridDim.x, red);
+  const double dx2         = gather_partials(parts + gridDim.x, gridDim.x, red);
+  const double dy2         = gather_partials(part_dy2, n_part_dy2, red);
+  if (threadIdx.x != 0) return;
+#pragma unroll
+  for (int r = 0; r < DIST_MAX_PEERS; ++r)
+    if (r < world) {
+      double* o = scal_peers.p[r];
+      o[0]      = interaction;
+      o[1]      = dx2;
+      o[2]      = dy2;
+    }
+  __threadfence_system();
+#pragma unroll
+  for (int r = 0; r < DIST_MAX_PEERS; ++r)
+    if (r < world) st_release_sys(flags.p[r] + DIST_FLAG_SCALARS + rank, epoch);
+}
+
+// Setup of that transport: the rows J_h of the global (scaled) A^T are assembled on rank h from the transposes A_g^T of the
+// row blocks, read straight from the peers' memory (rank order = ascending global row index = the order a single-GPU
+// transpose gives).  offs / idxs / vals: peer-mapped CSR arrays of every rank's A_g^T (n rows, m_g columns).
+struct peer_csr_t {
+  const int* off[DIST_MAX_PEERS];
+  const int* idx[DIST_MAX_PEERS];
+  const double* val[DIST_MAX_PEERS];
+  int row0[DIST_MAX_PEERS];  // first global constraint row of every rank
+};
+__global__ void __launch_bounds__(EW_THREADS) k_slice_row_counts(int rows, int j0, peer_csr_t src, int world, int* __restrict__ cnt)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= rows; j += stride) {
+    int c = 0;
+    if (j < rows) {
+#pragma unroll
+      for (int g = 0; g < DIST_MAX_PEERS; ++g)
+        if (g < world) c += src.off[g][j0 + j + 1] - src.off[g][j0 + j];
+    }
+    cnt[j] = c;
+  }
+}
+__global__ void __launch_bounds__(EW_THREADS) k_slice_fill(int rows, int j0, peer_csr_t src, int world,
+                                                           const int* __restrict__ soff, int* __restrict__ sidx,
+                                                           double* __restrict__ sval)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < rows; j += stride) {
+    int p = soff[j];
+#pragma unroll
+    for (int g = 0; g < DIST_MAX_PEERS; ++g)
+      if (g < world) {
+        const int lo = src.off[g][j0 + j], hi = src.off[g][j0 + j + 1];
+        for (int e = lo; e < hi; ++e, ++p) {
+          sidx[p] = src.idx[g][e] + src.row0[g];
+          sval[p] = src.val[g][e];
+        }
+      }
+  }
+}
+
+// Packed exchange of the gather transport: a rank reads only the entries of xbar (y') whose column (row) occurs in its rows
+// of A (of A^T) — 1 - exp(-nnz_g / n) of them for uniformly random columns, 63 % at 8 ranks of configs[3] — so only those
+// travel, into a buffer indexed by RANK AMONG THE NEEDED ENTRIES (ascending, so row entries stay sorted).
+__global__ void __launch_bounds__(EW_THREADS) k_mark_indices(int nnz, const int* __restrict__ idx, int* __restrict__ flag)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) flag[idx[e]] = 1;
+}
+__global__ void __launch_bounds__(EW_THREADS) k_fill_int(int n, int* __restrict__ v, int value)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = value;
+}
+// pos[j] = slot of entry j in the packed buffer, -1 when it is not needed (scan = exclusive sum of flag)
+__global__ void __launch_bounds__(EW_THREADS) k_packed_positions(int n, const int* __restrict__ flag, const int* __restrict__ scan,
+                                                                 int* __restrict__ pos)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) pos[j] = flag[j] ? scan[j] : -1;
+}
+__global__ void __launch_bounds__(EW_THREADS) k_remap_indices(int nnz, const int* __restrict__ idx_in, const int* __restrict__ pos,
+                                                              int* __restrict__ idx_out)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) idx_out[e] = pos[idx_in[e]];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,7 +606,9 @@ __global__ void __launch_bounds__(EW_THREADS) k_primal_step_bcast(pdhg_ctl_t* __
                                                                   peer_ptrs_t xbar_peers,
                                                                   peer_flags_t flags,
                                                                   int world,
-                                                                  int rank)
+                                                                  int rank,
+                                                                  const int* __restrict__ send = nullptr,
+                                                                  int send_stride = 0)
 {
   if (!ctl->active) return;
   const unsigned long long epoch = (unsigned long long)ctl->attempts + 1ull;
@@ -468,9 +628,18 @@ __global__ void __launch_bounds__(EW_THREADS) k_primal_step_bcast(pdhg_ctl_t* __
     next                  = fmax(fmin(next, ld_stream(u + j)), ld_stream(l + j));
     xn[j]                 = next;
     const double xb       = next - xj + next;
+    if (send) {  // gather transport: packed xbar, send[r * send_stride + j] = slot in rank r's buffer, -1 if r never reads x_j
 #pragma unroll
-    for (int r = 0; r < DIST_MAX_PEERS; ++r)
-      if (r < world) xbar_peers.p[r][j] = xb;
+      for (int r = 0; r < DIST_MAX_PEERS; ++r)
+        if (r < world) {
+          const int d = __ldg(send + (size_t)r * send_stride + j);
+          if (d >= 0) xbar_peers.p[r][d] = xb;
+        }
+    } else {
+#pragma unroll
+      for (int r = 0; r < DIST_MAX_PEERS; ++r)
+        if (r < world) xbar_peers.p[r][j] = xb;
+    }
   }
   peer_signal_grid_done(&ctl->ticket[1], flags, world, DIST_FLAG_XBAR + rank, epoch);
 }

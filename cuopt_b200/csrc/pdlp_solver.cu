@@ -169,6 +169,7 @@ void csr_transpose_device(int rows, int cols, int nnz, const int* off, const int
 void sort_keys_with_index(int count, const double* keys_in, double* keys_out, const int* vals_in, int* vals_out,
                           cudaStream_t stream);  // csr_transpose.cu (CUB)
 void inclusive_sum_in_place(int count, double* values, cudaStream_t stream);
+void exclusive_sum_int(int count, const int* in, int* out, cudaStream_t stream);
 void csr_split_columns_offsets(int rows, const int* off, const int* idx, int width, int n_blocks, int* const* blk_off,
                                int* blk_nnz_host, cudaStream_t stream);  // csr_transpose.cu
 void csr_split_columns_fill(int rows, const int* off, const int* idx, const double* val, int width, int n_blocks,
@@ -331,9 +332,47 @@ struct pdlp_solver_t::impl_t {
   bool sharded() const { return dist != nullptr && dist->world > 1; }
   // Transport of the sharded PDHG attempt: 0 = replicated primal side + one all-reduce (scheme (i)),
   // 1 = column slices + NCCL all-gather / reduce-scatter (scheme (ii)), 2 = column slices + NVLink peer stores
-  // issued by the producing kernels (scheme (ii), no NCCL in the loop).  CUOPT_B200_DIST_MODE=allreduce|nccl|p2p.
-  enum { DIST_ALLREDUCE = 0, DIST_NCCL_SLICES = 1, DIST_P2P = 2 };
+  // issued by the producing kernels (scheme (ii), no NCCL in the loop), 3 = "gather" (default): every rank also owns the
+  // rows J_g of the global A^T, so BOTH products take all-gathered inputs (xbar from K1, y' from K2, by peer stores) and
+  // there are no partial products at all.  CUOPT_B200_DIST_MODE=allreduce|nccl|p2p|gather.
+  enum { DIST_ALLREDUCE = 0, DIST_NCCL_SLICES = 1, DIST_P2P = 2, DIST_GATHER = 3 };
   int dist_mode = DIST_ALLREDUCE;
+  bool peer_transport() const { return dist_mode == DIST_P2P || dist_mode == DIST_GATHER; }
+  // gather transport: global row offsets of the ranks, the all-gathered y', this rank's rows of the global scaled A^T
+  int row0[DIST_MAX_PEERS + 1] = {};
+  int m_total = 0;
+  dvec<double> yfull, t_slice;
+  void* yfull_peer[DIST_MAX_PEERS] = {};
+  peer_ptrs_t p_yfull{};
+  csr_dev_t ATslice;
+  // packed exchange: Ahot = the scaled A_g with column indices renumbered to the entries of xbar this rank reads; sendX / sendY
+  // = per destination rank, where each of MY xbar / y' entries lives in ITS packed buffer (-1: it never reads that entry)
+  csr_dev_t Ahot;
+  dvec<int> sendX, sendY;
+  int cntX = 0, cntY = 0;
+  bool dist_pack = true;  // CUOPT_B200_DIST_PACK=0: identity packing (everything travels), for comparison
+  const csr_dev_t& hot_A() const { return (dist != nullptr && dist->world > 1 && dist_mode == DIST_GATHER) ? Ahot : As; }
+  // CUOPT_B200_DIST_TRACE=1: CUDA-event time of every kernel slot of the sharded attempt (waiting for the peers' flags
+  // included), printed per rank when the solver goes away.  Turns the CUDA graphs off and synchronises once per attempt.
+  bool dist_trace = false;
+  cudaEvent_t tr_ev[6] = {};
+  double tr_acc[5] = {};
+  long tr_count = 0;
+  void tr_tick(int i)
+  {
+    if (dist_trace) cudaEventRecord(tr_ev[i], stream);
+  }
+  void tr_close(int last)
+  {
+    if (!dist_trace) return;
+    cudaEventSynchronize(tr_ev[last]);
+    for (int i = 0; i < last; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tr_ev[i], tr_ev[i + 1]);
+      tr_acc[i] += ms;
+    }
+    ++tr_count;
+  }
   int nslice = 0, n_pad = 0, slice_j0 = 0, slice_n = 0, grid_slice = 1;
   dvec<double> rs_buf, stage, scal;
   dvec<unsigned long long> d_flags;
@@ -374,7 +413,7 @@ struct pdlp_solver_t::impl_t {
     std::vector<int> grid;  // per block, for the schedule (wide or not) its pass uses
     bool on() const { return B > 1; }
   };
-  gather_blocks_t blkA, blkAT;
+  gather_blocks_t blkA, blkAT, blkATslice;
   dvec<double> t_m, t_n;
   size_t gather_block_bytes = 40u << 20;  // measured optimum at configs[3] (profiles/r1/gather_block_sweep_c4.txt)
   int n_part_dy2 = 1;  // CTAs that publish ||dy||^2 partials: grid_k2 (fused K2) or grid_m (blocked K2 epilogue)
@@ -406,6 +445,7 @@ struct pdlp_solver_t::impl_t {
     dist->close_peers(stage_peer);
     dist->close_peers(scal_peer);
     dist->close_peers(flag_peer);
+    dist->close_peers(yfull_peer);
     peers_open = false;
     if (collective) {
       dist->allreduce(d_scalar.data(), 1, true, stream);  // barrier
@@ -420,6 +460,11 @@ struct pdlp_solver_t::impl_t {
       std::fprintf(stderr, "[cuopt-b200 trace] so far in this process: %ld cudaMalloc %.1f ms (%.2f GB), %ld cudaFree %.1f ms\n",
                    a.n_malloc, 1e3 * a.malloc_s, a.bytes * 1e-9, a.n_free, 1e3 * a.free_s);
     }
+    if (dist_trace && tr_count > 0)
+      std::fprintf(stderr, "[cuopt-b200 dist trace] rank %d of %d, mode %d, %ld attempts: K1 %.1f us, K2 %.1f us, K3 %.1f us, rule %.1f us "
+                   "(each slot includes the wait for the peers' flags)\n", dist->rank, dist->world, dist_mode, tr_count,
+                   1e3 * tr_acc[0] / tr_count, 1e3 * tr_acc[1] / tr_count, 1e3 * tr_acc[2] / tr_count, 1e3 * tr_acc[3] / tr_count);
+    for (auto& e : tr_ev) if (e) cudaEventDestroy(e);
     close_peer_memory(false);
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
     if (ev_a) cudaEventDestroy(ev_a);
@@ -619,20 +664,36 @@ struct pdlp_solver_t::impl_t {
   {
     dist_buf.resize(2 * (size_t)std::max(n, n_pad) + 8);
     dist_buf.zero(stream);
-    dist_mode = DIST_P2P;
+    dist_mode = DIST_GATHER;
     if (const char* e = std::getenv("CUOPT_B200_DIST_MODE")) {
       const std::string v(e);
       if (v == "allreduce") dist_mode = DIST_ALLREDUCE;
       else if (v == "nccl") dist_mode = DIST_NCCL_SLICES;
       else if (v == "p2p") dist_mode = DIST_P2P;
-      else throw lp_error(error_type_t::InvalidArgument, "CUOPT_B200_DIST_MODE must be allreduce, nccl or p2p");
+      else if (v == "gather") dist_mode = DIST_GATHER;
+      else throw lp_error(error_type_t::InvalidArgument, "CUOPT_B200_DIST_MODE must be allreduce, nccl, p2p or gather");
+    }
+    {  // global row offsets of the ranks (the row blocks are contiguous and in rank order)
+      dvec<double> cnt((size_t)dist->world);
+      cnt.zero(stream);
+      const double mine = (double)m;
+      CUOPT_CUDA_TRY(cudaMemcpyAsync(cnt.data() + dist->rank, &mine, sizeof(double), cudaMemcpyHostToDevice, stream));
+      dist->allgather(cnt.data(), 1, stream);
+      std::vector<double> h((size_t)dist->world);
+      cnt.download(h.data(), stream);
+      sync();
+      long long tot = 0;
+      for (int r = 0; r < dist->world; ++r) { row0[r] = (int)tot; tot += (long long)h[r]; }
+      if (tot > 0x7fffffffLL) throw lp_error(error_type_t::ValidationError, "more than 2^31 - 1 constraint rows over all ranks");
+      row0[dist->world] = m_total = (int)tot;
     }
     grid_slice = ew_grid(std::max(nslice, 1), sms);
     scal.resize(4 * DIST_MAX_PEERS);
     scal.zero(stream);
     if (dist_mode == DIST_NCCL_SLICES) { rs_buf.resize(nslice); rs_buf.zero(stream); }
-    if (dist_mode == DIST_P2P) {
-      stage.resize((size_t)nslice * dist->world);
+    if (peer_transport()) {
+      if (dist_mode == DIST_P2P) stage.resize((size_t)nslice * dist->world);
+      else { stage.resize(32); yfull.resize((size_t)std::max(m_total, 32)); yfull.zero(stream); }
       stage.zero(stream);
       d_flags.resize(DIST_FLAG_COUNT);
       d_flags.zero(stream);
@@ -641,22 +702,31 @@ struct pdlp_solver_t::impl_t {
       ok      = ok && dist->open_peers(stage.data(), stage_peer, stream);
       ok      = ok && dist->open_peers(scal.data(), scal_peer, stream);
       ok      = ok && dist->open_peers(d_flags.data(), flag_peer, stream);
+      if (dist_mode == DIST_GATHER) ok = ok && dist->open_peers(yfull.data(), yfull_peer, stream);
       if (!ok) {  // unanimous (open_peers agrees across ranks): no peer access on this box -> NCCL transport
         dist->close_peers(xbar_peer); dist->close_peers(stage_peer); dist->close_peers(scal_peer);
+        dist->close_peers(flag_peer); dist->close_peers(yfull_peer);
         dist_mode = DIST_NCCL_SLICES;
         rs_buf.resize(nslice);
         rs_buf.zero(stream);
       } else {
         peers_open = true;
         for (int r = 0; r < dist->world; ++r) {
-          p_xbar.p[r]  = static_cast<double*>(xbar_peer[r]) + slice_j0;
+          p_xbar.p[r]  = static_cast<double*>(xbar_peer[r]) + (dist_mode == DIST_GATHER ? 0 : slice_j0);
           p_stage.p[r] = static_cast<double*>(stage_peer[r]) + (size_t)dist->rank * nslice;
           p_scal.p[r]  = static_cast<double*>(scal_peer[r]) + 4 * dist->rank;
           p_flags.p[r] = static_cast<unsigned long long*>(flag_peer[r]);
+          if (dist_mode == DIST_GATHER) p_yfull.p[r] = static_cast<double*>(yfull_peer[r]);
         }
       }
     }
-    if (dist_mode != DIST_P2P) {
+    if (const char* e = std::getenv("CUOPT_B200_DIST_TRACE")) dist_trace = e[0] == '1';
+    if (const char* e = std::getenv("CUOPT_B200_DIST_PACK")) dist_pack = e[0] != '0';
+    if (dist_trace) {
+      use_graphs = false;
+      for (auto& e : tr_ev) CUOPT_CUDA_TRY(cudaEventCreate(&e));
+    }
+    if (!peer_transport()) {
       use_graphs  = false;  // NCCL calls between the kernels
       p_scal.p[0] = scal.data();
     }
@@ -752,8 +822,12 @@ struct pdlp_solver_t::impl_t {
     fill_bicsr_values(As, stream, sms);
     fill_bicsr_values(ATs, stream, sms);
     trace.mark("scale problem + scaled BICSR values");
-    build_gather_blocks(As, blkA, t_m);
-    build_gather_blocks(ATs, blkAT, t_n);
+    if (sharded() && dist_mode == DIST_GATHER) {
+      build_gather_transport();  // packed A_g, rows J_g of the global A^T; the hot loop never multiplies by A_g^T
+    } else {
+      build_gather_blocks(As, blkA, t_m);
+      build_gather_blocks(ATs, blkAT, t_n);
+    }
     trace.mark("gather blocks");
     n_part_dy2 = k2_grid();  // CTAs of the kernel that runs the dual row epilogue
     if (!hp.compute_initial_step_size_before_scaling) step = initial_step_size(As);
@@ -862,6 +936,120 @@ struct pdlp_solver_t::impl_t {
     sol.warm_start                   = w;
   }
 
+  // Gather transport, setup (collective): this rank's rows J_g of the global scaled A^T, assembled from the scaled A_h^T of
+  // every rank through peer reads (k_slice_row_counts / k_slice_fill) as plain CSR with GLOBAL row ids as column indices;
+  // returns its host row offsets (build_gather_transport renumbers the columns and builds the BICSR form).
+  std::vector<int> build_slice_transpose()
+  {
+    const int G = dist->world;
+    void *offp[DIST_MAX_PEERS] = {}, *idxp[DIST_MAX_PEERS] = {}, *valp[DIST_MAX_PEERS] = {};
+    bool ok = dist->open_peers(const_cast<int*>(ATs.off_ptr()), offp, stream);
+    ok      = ok && dist->open_peers(const_cast<int*>(ATs.idx_ptr()), idxp, stream);
+    ok      = ok && dist->open_peers(ATs.val.data(), valp, stream);
+    if (!ok) throw lp_error(error_type_t::RuntimeError, "gather transport: peer mapping of the transposed row blocks failed");
+    peer_csr_t src{};
+    for (int r = 0; r < G; ++r) {
+      src.off[r]  = static_cast<const int*>(offp[r]);
+      src.idx[r]  = static_cast<const int*>(idxp[r]);
+      src.val[r]  = static_cast<const double*>(valp[r]);
+      src.row0[r] = row0[r];
+    }
+    ATslice      = csr_dev_t{};
+    ATslice.rows = slice_n;
+    ATslice.cols = m_total;
+    dvec<int> cnt((size_t)slice_n + 1);
+    ATslice.off.resize((size_t)slice_n + 1);
+    const int g = ew_grid(slice_n + 1, sms);
+    k_slice_row_counts<<<g, EW_THREADS, 0, stream>>>(slice_n, slice_j0, src, G, cnt.data());
+    exclusive_sum_int(slice_n + 1, cnt.data(), ATslice.off.data(), stream);
+    std::vector<int> hoff((size_t)slice_n + 1);
+    ATslice.off.download(hoff.data(), stream);
+    sync();
+    ATslice.nnz = hoff[slice_n];
+    ATslice.idx.resize((size_t)std::max(ATslice.nnz, 1));
+    ATslice.val.resize((size_t)std::max(ATslice.nnz, 1));
+    k_slice_fill<<<g, EW_THREADS, 0, stream>>>(slice_n, slice_j0, src, G, ATslice.off.data(), ATslice.idx.data(),
+                                               ATslice.val.data());
+    check_launch();
+    sync();
+    // nobody may touch / free its A_h^T while a peer still reads it: barrier, then unmap
+    dist->allreduce(d_scalar.data(), 1, true, stream);
+    sync();
+    dist->close_peers(offp); dist->close_peers(idxp); dist->close_peers(valp);
+    return hoff;
+  }
+
+  // Which of `count` entries occur among `nnz` indices -> pos[j] = slot in the packed buffer or -1 (identity when packing is
+  // off); returns the packed length.  pos has `padded` >= count entries (the pad is -1).
+  int packed_positions(int count, int padded, int nnz, const int* idx, dvec<int>& pos)
+  {
+    dvec<int> flag((size_t)padded + 1), scan((size_t)padded + 1);
+    flag.zero(stream);
+    if (dist_pack) {
+      if (nnz > 0) k_mark_indices<<<ew_grid(nnz, sms), EW_THREADS, 0, stream>>>(nnz, idx, flag.data());
+    } else if (count > 0) {
+      k_fill_int<<<ew_grid(count, sms), EW_THREADS, 0, stream>>>(count, flag.data(), 1);
+    }
+    exclusive_sum_int(padded + 1, flag.data(), scan.data(), stream);
+    pos.resize((size_t)std::max(padded, 1));
+    if (padded > 0) k_packed_positions<<<ew_grid(padded, sms), EW_THREADS, 0, stream>>>(padded, flag.data(), scan.data(), pos.data());
+    int total = 0;
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(&total, scan.data() + padded, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    check_launch();
+    sync();
+    return total;
+  }
+  // every rank's pos array (same length everywhere) -> mine[g * count + i] = peer g's pos[first + i]  (collective)
+  void exchange_positions(dvec<int>& pos, int first, int count, dvec<int>& mine)
+  {
+    const int G = dist->world;
+    void* peers[DIST_MAX_PEERS] = {};
+    if (!dist->open_peers(pos.data(), peers, stream))
+      throw lp_error(error_type_t::RuntimeError, "gather transport: peer mapping of the packing tables failed");
+    mine.resize((size_t)std::max(count, 1) * G);
+    for (int g = 0; g < G && count > 0; ++g)
+      CUOPT_CUDA_TRY(cudaMemcpyAsync(mine.data() + (size_t)g * count, static_cast<const int*>(peers[g]) + first,
+                                     (size_t)count * sizeof(int), cudaMemcpyDefault, stream));
+    sync();
+    dist->allreduce(d_scalar.data(), 1, true, stream);  // nobody frees its table while a peer still reads it
+    sync();
+    dist->close_peers(peers);
+  }
+  void build_gather_transport()
+  {
+    // xbar side: the columns this rank's rows of A touch
+    dvec<int> posX, posY;
+    cntX = packed_positions(n, n_pad, A.nnz, A.idx.data(), posX);
+    Ahot      = csr_dev_t{};
+    Ahot.rows = m;
+    Ahot.cols = std::max(cntX, 1);
+    Ahot.nnz  = A.nnz;
+    Ahot.off.copy_from(A.off, stream);
+    Ahot.idx.resize((size_t)std::max(A.nnz, 1));
+    if (A.nnz > 0) k_remap_indices<<<ew_grid(A.nnz, sms), EW_THREADS, 0, stream>>>(A.nnz, A.idx.data(), posX.data(), Ahot.idx.data());
+    Ahot.val.copy_from(As.val, stream);
+    {
+      std::vector<int> hoff((size_t)m + 1);
+      A.off.download(hoff.data(), stream);
+      sync();
+      build_bicsr(Ahot, hoff, stream, sms);
+    }
+    build_gather_blocks(Ahot, blkA, t_m);
+    exchange_positions(posX, slice_j0, nslice, sendX);
+    // y' side: the constraint rows this rank's rows of the global A^T touch
+    std::vector<int> hoff = build_slice_transpose();
+    cntY = packed_positions(m_total, m_total, ATslice.nnz, ATslice.idx.data(), posY);
+    if (ATslice.nnz > 0)
+      k_remap_indices<<<ew_grid(ATslice.nnz, sms), EW_THREADS, 0, stream>>>(ATslice.nnz, ATslice.idx.data(), posY.data(),
+                                                                            ATslice.idx.data());
+    ATslice.cols = std::max(cntY, 1);
+    build_bicsr(ATslice, hoff, stream, sms);
+    build_gather_blocks(ATslice, blkATslice, t_slice);
+    exchange_positions(posY, row0[dist->rank], m, sendY);
+    check_launch();
+    sync();
+  }
+
   // ------------------------------------------------------------------------------ PDHG batches
   // Cuts the scaled matrix M into column blocks (device, stable) when the vector it gathers from exceeds the block size.
   void build_gather_blocks(const csr_dev_t& M, gather_blocks_t& g, dvec<double>& t)
@@ -917,10 +1105,11 @@ struct pdlp_solver_t::impl_t {
   }
   // K2: one fused kernel; with gather blocking (B - 1) payload-free passes over the first column blocks, then the fused kernel
   // on the last block continuing their running sum.  wait_flags: peer transport (xbar slices of the peers)
-  void enqueue_k2(const unsigned long long* wait_flags, int n_wait)
+  // bcast: gather transport, the fused kernel also stores y' into every rank's all-gathered y' buffer
+  void enqueue_k2(const unsigned long long* wait_flags, int n_wait, bool bcast = false)
   {
     const bool blocked  = blkA.on();
-    const csr_dev_t& L  = blocked ? blkA.blk[blkA.B - 1] : As;
+    const csr_dev_t& L  = blocked ? blkA.blk[blkA.B - 1] : hot_A();
     const int npre      = fused_npre(L);
     const int grid      = spmv_grid(L, npre);
     const double* t     = blocked ? t_m.data() : nullptr;
@@ -930,13 +1119,22 @@ struct pdlp_solver_t::impl_t {
   k_dual_step<INIT, NPRE><<<grid, BICSR_THREADS, 0, stream>>>(d_ctl.data(), L.view(), xbar.data(), ybuf[0].data(),       \
                                                               ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(),      \
                                                               part_dy2.data(), wf, n_wait, t)
-    if (blocked) { if (npre > 1) CUOPT_K2(true, 2); else CUOPT_K2(true, 1); }
+#define CUOPT_K2B(INIT, NPRE)                                                                                            \
+  k_dual_step<INIT, NPRE, true><<<grid, BICSR_THREADS, 0, stream>>>(d_ctl.data(), L.view(), xbar.data(), ybuf[0].data(), \
+                                                                    ybuf[1].data(), lcs.data(), ucs.data(), sum_y.data(), \
+                                                                    part_dy2.data(), wf, n_wait, t, p_yfull, p_flags,     \
+                                                                    dist->world, dist->rank, sendY.data(), m)
+    if (bcast) {
+      if (blocked) { if (npre > 1) CUOPT_K2B(true, 2); else CUOPT_K2B(true, 1); }
+      else { if (npre > 1) CUOPT_K2B(false, 2); else CUOPT_K2B(false, 1); }
+    } else if (blocked) { if (npre > 1) CUOPT_K2(true, 2); else CUOPT_K2(true, 1); }
     else { if (npre > 1) CUOPT_K2(false, 2); else CUOPT_K2(false, 1); }
+#undef CUOPT_K2B
 #undef CUOPT_K2
   }
   int k2_grid() const
   {
-    const csr_dev_t& L = blkA.on() ? blkA.blk[blkA.B - 1] : As;
+    const csr_dev_t& L = blkA.on() ? blkA.blk[blkA.B - 1] : hot_A();
     return spmv_grid(L, fused_npre(L));
   }
   // K3 on one GPU: same structure, the step rule runs in the last CTA of the fused kernel
@@ -961,6 +1159,7 @@ struct pdlp_solver_t::impl_t {
   {
     const int k2 = blkA.on() ? blkA.B : 1;
     if (!sharded()) return 1 + k2 + (blkAT.on() ? blkAT.B : 1);
+    if (dist_mode == DIST_GATHER) return 1 + k2 + (blkATslice.on() ? blkATslice.B : 1) + 1;
     const int k3p = blkAT.on() ? blkAT.B + (dist_mode == DIST_P2P ? 1 : 0) : 1;
     return 1 + k2 + k3p + (dist_mode == DIST_ALLREDUCE ? 2 : 2);
   }
@@ -986,11 +1185,41 @@ struct pdlp_solver_t::impl_t {
   {
     const int j0 = slice_j0, G = dist->world, rk = dist->rank;
     double *x0 = xbuf[0].data() + j0, *x1 = xbuf[1].data() + j0, *a0 = atybuf[0].data() + j0, *a1 = atybuf[1].data() + j0;
+    if (dist_mode == DIST_GATHER) {
+      tr_tick(0);
+      k_primal_step_bcast<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, x0, x1, a0, a1, cs.data() + j0,
+                                                                 ls.data() + j0, us.data() + j0, sum_x.data() + j0, p_xbar,
+                                                                 p_flags, G, rk, sendX.data(), nslice);
+      tr_tick(1);
+      enqueue_k2(d_flags.data() + DIST_FLAG_XBAR, G, true);
+      tr_tick(2);
+      // K3 on this rank's rows of the global A^T, gathering from the all-gathered y' (the first kernel that touches it waits
+      // for the G y' flags); its last CTA sends this rank's three scalars to everyone
+      const bool blocked = blkATslice.on();
+      const csr_dev_t& L = blocked ? blkATslice.blk[blkATslice.B - 1] : ATslice;
+      const int grid     = spmv_grid(L, 1);
+      const unsigned long long* yflags = d_flags.data() + DIST_FLAG_PARTIAL;
+      if (blocked) launch_block_passes(blkATslice, blkATslice.B - 1, yfull.data(), yfull.data(), 0, t_slice.data(), yflags, G);
+#define CUOPT_K3S(INIT)                                                                                                     \
+  k_transpose_step_slice<INIT, 1><<<grid, BICSR_THREADS, 0, stream>>>(                                                      \
+    d_ctl.data(), L.view(), yfull.data(), x0, x1, a0, a1, part_k3.data(), part_dy2.data(), n_part_dy2,                      \
+    blocked ? t_slice.data() : nullptr, blocked ? nullptr : yflags, G, p_scal, p_flags, G, rk)
+      if (blocked) CUOPT_K3S(true); else CUOPT_K3S(false);
+#undef CUOPT_K3S
+      tr_tick(3);
+      k_step_rule_gather<<<1, 32, 0, stream>>>(d_ctl.data(), scal.data(), G, d_flags.data() + DIST_FLAG_SCALARS);
+      tr_tick(4);
+      tr_close(4);
+      return;
+    }
     if (dist_mode == DIST_P2P) {
+      tr_tick(0);
       k_primal_step_bcast<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, x0, x1, a0, a1, cs.data() + j0,
                                                                  ls.data() + j0, us.data() + j0, sum_x.data() + j0, p_xbar,
                                                                  p_flags, G, rk);
+      tr_tick(1);
       enqueue_k2(d_flags.data() + DIST_FLAG_XBAR, G);
+      tr_tick(2);
       if (blkAT.on()) {
         launch_block_passes(blkAT, blkAT.B, ybuf[0].data(), ybuf[1].data(), 1, t_n.data(), nullptr, 0);
         k_scatter_partials<<<grid_n, EW_THREADS, 0, stream>>>(d_ctl.data(), n, t_n.data(), p_stage, nslice, p_flags, G, rk);
@@ -1000,7 +1229,10 @@ struct pdlp_solver_t::impl_t {
       k_interaction_slice<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, stage.data(), G, (size_t)nslice, x0, x1,
                                                                  a0, a1, part_k3.data(), part_dy2.data(), n_part_dy2,
                                                                  d_flags.data() + DIST_FLAG_PARTIAL, p_scal, p_flags, G, rk);
+      tr_tick(3);
       k_step_rule_gather<<<1, 32, 0, stream>>>(d_ctl.data(), scal.data(), G, d_flags.data() + DIST_FLAG_SCALARS);
+      tr_tick(4);
+      tr_close(4);
       return;
     }
     k_primal_step<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, x0, x1, a0, a1, cs.data() + j0,

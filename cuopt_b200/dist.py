@@ -102,3 +102,40 @@ def reference_protocol_step_sliced(shard, rank, world, x_slice, x_next_slice, at
     for g in range(world):
         tot += table[g]
     return y_next, aty_next_slice, float(tot[0]), float(tot[1]), float(tot[2])
+
+
+def slice_of_global_transpose(local_transposes, row_starts, j0, j1):
+    """What the gather transport's setup builds on the device (k_slice_row_counts / k_slice_fill): rows [j0, j1) of the
+    GLOBAL A^T from the transposes A_g^T (scipy csr, n x m_g) of the row blocks, concatenated per row in rank order with
+    the column indices shifted to global constraint rows."""
+    import scipy.sparse as sp
+    m_total = int(row_starts[-1])
+    blocks = [sp.csr_matrix(t[j0:j1]) for t in local_transposes]
+    return sp.hstack(blocks, format="csr") if blocks else sp.csr_matrix((j1 - j0, m_total))
+
+
+def reference_protocol_step_gather(shard, at_slice, rank, world, x_slice, x_next_slice, aty_slice, y_local, sigma, lc, uc,
+                                   allgather_x, allgather_y, allgather_scalars):
+    """One attempt of the gather transport (the default) in numpy: this rank holds rows R_g of A, rows
+    J_g of the global A^T (`at_slice`, n_g x m) and the slice J_g of x, x', A^T y.  Exchanges: xbar slices -> everyone,
+    y' row blocks -> everyone (`allgather_y` returns the m global rows in rank order), three scalars per rank -> everyone
+    (summed in rank order).  No partial products: A^T y' on the slice is a complete row sum."""
+    A = shard
+    n = A.shape[1]
+    nslice, bounds = slice_bounds(n, world)
+    j0, j1 = bounds[rank]
+    xbar_slice = np.zeros(nslice)
+    xbar_slice[: j1 - j0] = x_next_slice - x_slice + x_next_slice
+    xbar = allgather_x(xbar_slice)[:n]
+    ybar = y_local - sigma * (A @ xbar)
+    y_next = np.maximum(ybar + sigma * lc, np.minimum(ybar + sigma * uc, 0.0))
+    dy = y_next - y_local
+    y_full = allgather_y(y_next)
+    aty_next_slice = at_slice @ y_full
+    dx = x_next_slice - x_slice
+    mine = np.array([float(dx @ (aty_next_slice - aty_slice)), float(dx @ dx), float(dy @ dy)])
+    table = allgather_scalars(mine)
+    tot = np.zeros(3)
+    for g in range(world):
+        tot += table[g]
+    return y_next, aty_next_slice, float(tot[0]), float(tot[1]), float(tot[2])

@@ -5,6 +5,8 @@
   * every rank derives bit-identical scalars from the all-reduced buffer (=> identical accept/reject decisions).
   * the column-sliced scheme (all-gather of xbar slices, rank-ordered reduce-scatter of the partials, rank-ordered sum
     of three scalars per rank) reproduces the same attempt and the same bits on every rank,
+  * the gather transport (rows of A and rows of the global A^T per rank, xbar and y' all-gathered, no partial products)
+    reproduces the same attempt, and its slice of A^T assembled from the transposed row blocks equals the real one,
   * the slice bounds tile [0, n) with 32-aligned slices.
 The CUDA side of the same protocols is exercised by tests/test_gpu_dist.py on >= 2 GPUs."""
 import os
@@ -97,7 +99,29 @@ def _worker(rank, world, port, q):
         g2 = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
         dist.all_gather(g2, torch.tensor([inter2, dx22, dy22], dtype=torch.float64))
         same2 = all(torch.equal(g2[0], t) for t in g2)
-        q.put((rank, bool(ok and ok2), bool(same and same2), r0, r1))
+        # gather transport (default): rows J_g of the global A^T assembled from the transposed row blocks, y' all-gathered
+        def allgather_y(v):  # ragged row blocks: pad to the longest, drop the pads
+            sizes = [int(b[g + 1] - b[g]) for g in range(world)]
+            pad = np.zeros(max(sizes)); pad[: len(v)] = v
+            g = [torch.zeros(max(sizes), dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(g, torch.from_numpy(pad))
+            return np.concatenate([g[k].numpy()[: sizes[k]] for k in range(world)])
+
+        transposes = [As[int(b[g]):int(b[g + 1])].T.tocsr() for g in range(world)]  # what every rank holds: its own A_g^T
+        at_slice = cdist.slice_of_global_transpose(transposes, b, j0, j1)
+        assert (at_slice != As.T.tocsr()[j0:j1]).nnz == 0
+        y3, aty3, inter3, dx23, dy23 = cdist.reference_protocol_step_gather(
+            As[r0:r1].tocsr(), at_slice, rank, world, x[j0:j1], want["x_next"][j0:j1], aty[j0:j1], y[r0:r1], sigma,
+            lcs[r0:r1], ucs[r0:r1], allgather, allgather_y, allgather_scalars)
+        ok3 = (np.allclose(y3, want["y_next"][r0:r1], rtol=1e-12, atol=1e-13)
+               and np.allclose(aty3, want["aty_next"][j0:j1], rtol=1e-11, atol=1e-12)
+               and abs(dx23 - want["norm_dx2"]) <= 1e-11 * want["norm_dx2"]
+               and abs(dy23 - want["norm_dy2"]) <= 1e-11 * want["norm_dy2"]
+               and abs(inter3 - want["interaction"]) <= 1e-9 * max(abs(want["interaction"]), want["norm_dx2"]))
+        g3 = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(g3, torch.tensor([inter3, dx23, dy23], dtype=torch.float64))
+        same3 = all(torch.equal(g3[0], t) for t in g3)
+        q.put((rank, bool(ok and ok2 and ok3), bool(same and same2 and same3), r0, r1))
     finally:
         dist.destroy_process_group()
 

@@ -15,12 +15,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q, size, extra_cols, tol, mode, transport, block_bytes):
+def _worker(rank, world, port, q, size, extra_cols, tol, mode, transport, block_bytes, iteration_limit=0, nnz_per_row=8):
     import torch
     import torch.distributed as dist
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      CUOPT_B200_DIST_MODE=transport)
+                      CUOPT_B200_DIST_MODE=transport.split("-")[0])
+    if transport.endswith("-nopack"):  # gather transport with identity packing: every entry of xbar / y' travels
+        os.environ["CUOPT_B200_DIST_PACK"] = "0"
     if block_bytes:
         os.environ["CUOPT_B200_GATHER_BLOCK_BYTES"] = str(block_bytes)
     torch.cuda.set_device(rank)
@@ -28,10 +30,12 @@ def _worker(rank, world, port, q, size, extra_cols, tol, mode, transport, block_
     try:
         from cuopt_b200 import capi, lpgen
         from cuopt_b200 import dist as cdist
-        lp = lpgen.sparse_lp(size, size + extra_cols, 8, seed=21)
+        lp = lpgen.sparse_lp(size, size + extra_cols, nnz_per_row, seed=21)
         comm = cdist.bootstrap(rank, world, device=torch.device("cuda", rank))
         p, (r0, r1) = cdist.local_problem(lp, rank, world)
         s = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False, pdlp_solver_mode=mode)
+        if iteration_limit:
+            s.set("iteration_limit", iteration_limit)
         s.set("optimality_tolerance", tol)
         sol = capi.solve_distributed(p, s, comm)
         st = sol.stats()
@@ -43,12 +47,13 @@ def _worker(rank, world, port, q, size, extra_cols, tol, mode, transport, block_
         dist.destroy_process_group()
 
 
-def _solve_on_gpus(world, size, tol, mode, transport, extra_cols=0, block_bytes=0):
+def _solve_on_gpus(world, size, tol, mode, transport, extra_cols=0, block_bytes=0, iteration_limit=0, nnz_per_row=8):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, size, extra_cols, tol, mode, transport, block_bytes))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, size, extra_cols, tol, mode, transport, block_bytes,
+                                               iteration_limit, nnz_per_row))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -70,20 +75,44 @@ def _solve_on_gpus(world, size, tol, mode, transport, extra_cols=0, block_bytes=
     return res
 
 
-def _single_gpu(size, tol, mode):
+def _single_gpu(size, tol, mode, iteration_limit=0, nnz_per_row=8, extra_cols=0):
     from cuopt_b200 import capi, lpgen
-    lp = lpgen.sparse_lp(size, size, 8, seed=21)
+    lp = lpgen.sparse_lp(size, size + extra_cols, nnz_per_row, seed=21)
     p = capi.Problem.create_ranged(lp.offsets, lp.indices, lp.values, lp.con_lb, lp.con_ub, lp.c, lp.var_lb, lp.var_ub)
     s = capi.Settings(method=capi.CUOPT_METHOD_PDLP, log_to_console=False, pdlp_solver_mode=mode)
     s.set("optimality_tolerance", tol)
+    if iteration_limit:
+        s.set("iteration_limit", iteration_limit)
     one = capi.solve(p, s)
-    assert one.termination_status == 1
+    assert one.termination_status == (4 if iteration_limit else 1)
     return lp, one
 
 
-# transport of the sharded attempt: p2p = NVLink peer stores fused into the kernels (default), nccl = all-gather +
-# reduce-scatter, allreduce = replicated primal side (scheme (i))
-@pytest.mark.parametrize("mode,transport", [(1, "p2p"), (1, "nccl"), (1, "allreduce"), (3, "p2p")])
+@pytest.mark.parametrize("transport,nnz_per_row", [("gather", 8), ("gather", 2), ("gather-nopack", 2), ("p2p", 8), ("nccl", 8)])
+def test_sharded_iterates_track_the_single_gpu_iterates(transport, nnz_per_row):
+    """The strongest check of a transport: after the SAME number of iterations (no tolerance involved) the sharded solve holds
+    the iterate the single GPU holds, element-wise, up to the summation order of the row sums (block cuts of the row blocks
+    differ from those of the whole matrix; p2p / nccl also add the partial A_g^T y' in rank order).  A stale or torn xbar / y'
+    exchange shows up here as an O(1) difference.  The 2-per-row LP makes every rank need only part of the other ranks' slices."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    size, its = 40_000, 120  # crosses the every-iteration major iterations (k <= 10) and the ones at 40, 80, 120
+    res = _solve_on_gpus(2, size, 0.0, 1, transport, extra_cols=37, iteration_limit=its, nnz_per_row=nnz_per_row)
+    lp, one = _single_gpu(size, 0.0, 1, iteration_limit=its, nnz_per_row=nnz_per_row, extra_cols=37)
+    assert res[0]["its"] == one.stats().number_of_steps_taken == its
+    x1, y1 = one.primal(), one.dual()
+    y = np.concatenate([r["y"] for r in res])
+    scale_x, scale_y = np.abs(x1).max(), np.abs(y1).max()
+    assert np.abs(res[0]["x"] - x1).max() <= 1e-9 * scale_x
+    assert np.abs(y - y1).max() <= 1e-9 * scale_y
+    assert res[0]["obj"] == pytest.approx(one.stats().primal_objective, rel=1e-9, abs=1e-9)
+
+
+# transport of the sharded attempt: gather = every rank owns rows of A AND rows of the global A^T, both products take inputs
+# all-gathered by NVLink peer stores of the producing kernels (default); p2p = peer stores with partial A_g^T y' scattered to
+# the slice owners; nccl = all-gather + reduce-scatter; allreduce = replicated primal side (scheme (i))
+@pytest.mark.parametrize("mode,transport", [(1, "gather"), (1, "p2p"), (1, "nccl"), (1, "allreduce"), (3, "gather"), (3, "p2p")])
 def test_two_gpu_solve_matches_single_gpu(mode, transport):
     import torch
     if torch.cuda.device_count() < 2:
@@ -117,16 +146,17 @@ def test_four_and_eight_gpu_solve_matches_single_gpu(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     size, tol = 40_000, 1e-6
-    res = _solve_on_gpus(world, size, tol, 1, "p2p")
     lp, one = _single_gpu(size, tol, 1)
     st1 = one.stats()
-    assert res[0]["status"] == 1
-    assert res[0]["obj"] == pytest.approx(lp.optimal_objective, rel=1e-5)
-    assert res[0]["obj"] == pytest.approx(st1.primal_objective, rel=1e-5)
-    assert res[0]["dobj"] == pytest.approx(st1.dual_objective, rel=1e-5)
-    assert abs(res[0]["its"] - st1.number_of_steps_taken) <= max(40, 0.4 * st1.number_of_steps_taken)
-    y = np.concatenate([r["y"] for r in res])
-    assert y.shape[0] == lp.m and all(r["rows"][1] - r["rows"][0] == len(r["y"]) for r in res)
+    for transport in ("gather", "p2p"):
+        res = _solve_on_gpus(world, size, tol, 1, transport)
+        assert res[0]["status"] == 1
+        assert res[0]["obj"] == pytest.approx(lp.optimal_objective, rel=1e-5)
+        assert res[0]["obj"] == pytest.approx(st1.primal_objective, rel=1e-5)
+        assert res[0]["dobj"] == pytest.approx(st1.dual_objective, rel=1e-5)
+        assert abs(res[0]["its"] - st1.number_of_steps_taken) <= max(40, 0.4 * st1.number_of_steps_taken)
+        y = np.concatenate([r["y"] for r in res])
+        assert y.shape[0] == lp.m and all(r["rows"][1] - r["rows"][0] == len(r["y"]) for r in res)
 
 
 def test_peer_store_transport_is_deterministic_and_equals_nccl_transport():
@@ -149,7 +179,22 @@ def test_peer_store_transport_is_deterministic_and_equals_nccl_transport():
         assert all(np.array_equal(other[r]["y"], a[r]["y"]) for r in range(world))
 
 
-@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_gather_transport_is_deterministic_with_ragged_slices():
+    """The default transport reproduces itself bit for bit (no race between the peer stores of xbar / y', the flags and the
+    consuming kernels), also when the last column slice is shorter than the 32-aligned slice width."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    size, tol, world = 40_000, 1e-6, 2
+    a = _solve_on_gpus(world, size, tol, 1, "gather", 37)
+    b = _solve_on_gpus(world, size, tol, 1, "gather", 37)
+    assert a[0]["status"] == 1
+    assert b[0]["its"] == a[0]["its"] and b[0]["obj"] == a[0]["obj"] and b[0]["dobj"] == a[0]["dobj"]
+    assert np.array_equal(b[0]["x"], a[0]["x"])
+    assert all(np.array_equal(b[r]["y"], a[r]["y"]) for r in range(world))
+
+
+@pytest.mark.parametrize("transport", ["gather", "p2p", "nccl"])
 def test_two_gpu_solve_with_gather_blocking(transport):
     """The large-LP kernels (column-blocked passes + element-wise epilogues / scatter) inside the sharded attempt:
     forced on a small LP (4 blocks for A_g, 2 for A_g^T), they must reach the same optimum as the fused kernels."""
