@@ -1299,36 +1299,51 @@ __global__ void k_reset_after_restart(pdhg_ctl_t* ctl)
 }
 
 // =============================================================================================
-// One-time setup kernels: diagonal scaling (initial_scaling.cu:95-408).  Warp per row; not hot.
+// One-time setup kernels: diagonal scaling (initial_scaling.cu:95-408).  A group of W lanes per row; not hot.
 // =============================================================================================
 // mode 0: out[row] = max |(a * rs[row]) * cs[col]|        (Ruiz, :95-122)
 // mode 1: out[row] = sum |(a * rs[row]) * cs[col]|^power  (Pock-Chambolle, :177-252)
 // For A^T pass row_scale = variable scaling, col_scale = constraint scaling and `swap_assoc` keeps the
 // reference's association (a * constraint_scale) * variable_scale.
-__global__ void k_row_scaling_stat(int rows,
-                                   const int* __restrict__ off,
-                                   const int* __restrict__ idx,
-                                   const double* __restrict__ val,
-                                   const double* __restrict__ row_scale,
-                                   const double* __restrict__ col_scale,
-                                   int swap_assoc,
-                                   int mode,
-                                   double power,
-                                   double* __restrict__ out)
+// W lanes per row (W = 4, 8, 16 or 32, picked from the average row length: a warp per 8-entry row idles 24 lanes and took
+// 3 ms per pass at configs[3], 22 passes per solve); fixed xor tree over the W lanes.
+template <int W>
+__global__ void __launch_bounds__(256) k_row_scaling_stat(int rows,
+                                                          const int* __restrict__ off,
+                                                          const int* __restrict__ idx,
+                                                          const double* __restrict__ val,
+                                                          const double* __restrict__ row_scale,
+                                                          const double* __restrict__ col_scale,
+                                                          int swap_assoc,
+                                                          int mode,
+                                                          double power,
+                                                          double* __restrict__ out)
 {
-  const int lane = threadIdx.x & 31;
-  const int wpb  = blockDim.x >> 5;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
-    const double rs = row_scale[r];
+  const int sub    = threadIdx.x % W;
+  const int gpb    = blockDim.x / W;  // row groups per CTA
+  const int stride = gridDim.x * gpb;
+  // all lanes of a warp run the same number of rounds (the shuffles below need the whole warp)
+  const int rounds = (rows + stride - 1) / stride;
+  for (int it = 0; it < rounds; ++it) {
+    const int r     = it * stride + blockIdx.x * gpb + threadIdx.x / W;
+    const bool live = r < rows;
     double acc      = 0.0;
-    for (int p = off[r] + lane; p < off[r + 1]; p += 32) {
-      const double cs = col_scale[idx[p]];
-      const double a  = swap_assoc ? fabs((val[p] * cs) * rs) : fabs((val[p] * rs) * cs);
-      if (mode == 0) acc = fmax(acc, a);
-      else acc += pow(a, power);
+    if (live) {
+      const double rs = row_scale[r];
+      const int hi    = off[r + 1];
+      for (int p = off[r] + sub; p < hi; p += W) {
+        const double cs = col_scale[idx[p]];
+        const double a  = swap_assoc ? fabs((val[p] * cs) * rs) : fabs((val[p] * rs) * cs);
+        if (mode == 0) acc = fmax(acc, a);
+        else acc += pow(a, power);
+      }
     }
-    acc = mode == 0 ? warp_max(acc) : warp_sum(acc);
-    if (lane == 0) out[r] = acc;
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, acc, o);
+      acc                = mode == 0 ? fmax(acc, other) : acc + other;
+    }
+    if (live && sub == 0) out[r] = acc;
   }
 }
 // cum[i] = stat[i] > 0 ? cum[i] / sqrt(stat[i]) : cum[i]   (utils.cuh:123-129)
@@ -1341,18 +1356,21 @@ __global__ void k_apply_scaling_stat(int n, double* __restrict__ cum, const doub
   }
 }
 // val[p] = val[p] * row_scale[row] * col_scale[col]   (initial_scaling.cu:310-345; same expression for A and A^T)
-__global__ void k_scale_matrix(int rows,
-                               const int* __restrict__ off,
-                               const int* __restrict__ idx,
-                               double* __restrict__ val,
-                               const double* __restrict__ row_scale,
-                               const double* __restrict__ col_scale)
+template <int W>
+__global__ void __launch_bounds__(256) k_scale_matrix(int rows,
+                                                      const int* __restrict__ off,
+                                                      const int* __restrict__ idx,
+                                                      double* __restrict__ val,
+                                                      const double* __restrict__ row_scale,
+                                                      const double* __restrict__ col_scale)
 {
-  const int lane = threadIdx.x & 31;
-  const int wpb  = blockDim.x >> 5;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+  const int sub    = threadIdx.x % W;
+  const int gpb    = blockDim.x / W;
+  const int stride = gridDim.x * gpb;
+  for (int r = blockIdx.x * gpb + threadIdx.x / W; r < rows; r += stride) {
     const double rs = row_scale[r];
-    for (int p = off[r] + lane; p < off[r + 1]; p += 32) val[p] = val[p] * rs * col_scale[idx[p]];
+    const int hi    = off[r + 1];
+    for (int p = off[r] + sub; p < hi; p += W) val[p] = val[p] * rs * col_scale[idx[p]];
   }
 }
 // op 0: v *= s ; op 1: v = s == 0 ? 0 : v / s

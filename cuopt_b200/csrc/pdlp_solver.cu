@@ -732,6 +732,12 @@ struct pdlp_solver_t::impl_t {
     }
   }
 
+  // lanes per row of the setup kernels that walk plain CSR rows: the power of two at or above the average row length
+  static int row_group_width(const csr_dev_t& M)
+  {
+    const double avg = M.rows > 0 ? (double)M.nnz / M.rows : 0.0;
+    return avg <= 4.0 ? 4 : avg <= 8.0 ? 8 : avg <= 16.0 ? 16 : 32;
+  }
   // deterministic setup reduction, result on the host
   // `across_ranks`: the reduced quantity lives on row-sharded data (rows of A, lc/uc), combine over ranks too
   double setup_reduce(int kind, int count, const double* a, const double* b, double weight, bool across_ranks = false)
@@ -751,14 +757,19 @@ struct pdlp_solver_t::impl_t {
     nvtx_range_t nvtx_scope("compute_scaling_vectors (Ruiz + Pock-Chambolle)");
     k_fill<<<grid_m, EW_THREADS, 0, stream>>>(m, Dr.data(), 1.0);
     k_fill<<<grid_n, EW_THREADS, 0, stream>>>(n, Dc.data(), 1.0);
-    const int wg_m = std::max(1, std::min((m + 7) / 8, sms * 16));
-    const int wg_n = std::max(1, std::min((n + 7) / 8, sms * 16));
-    auto pass      = [&](int mode, double pr, double pc) {
+    auto stat = [&](const csr_dev_t& M, const double* rs, const double* cs, int swap, int mode, double power, double* out) {
+      const int w    = row_group_width(M);
+      const int grid = std::max(1, std::min((int)(((long long)M.rows * w + 255) / 256), sms * 16));
+#define CUOPT_STAT(W)                                                                                                   \
+  k_row_scaling_stat<W><<<grid, 256, 0, stream>>>(M.rows, M.off.data(), M.idx.data(), M.val.data(), rs, cs, swap, mode, \
+                                                  power, out)
+      if (w == 4) CUOPT_STAT(4); else if (w == 8) CUOPT_STAT(8); else if (w == 16) CUOPT_STAT(16); else CUOPT_STAT(32);
+#undef CUOPT_STAT
+    };
+    auto pass = [&](int mode, double pr, double pc) {
       // statistics of rows of A and of rows of A^T (columns of A), both with the OLD scaling vectors
-      k_row_scaling_stat<<<wg_m, 256, 0, stream>>>(m, A.off.data(), A.idx.data(), A.val.data(), Dr.data(), Dc.data(), 0,
-                                                   mode, pr, scratch_m.data());
-      k_row_scaling_stat<<<wg_n, 256, 0, stream>>>(n, AT.off.data(), AT.idx.data(), AT.val.data(), Dc.data(), Dr.data(),
-                                                   1, mode, pc, scratch_n.data());
+      stat(A, Dr.data(), Dc.data(), 0, mode, pr, scratch_m.data());
+      stat(AT, Dc.data(), Dr.data(), 1, mode, pc, scratch_n.data());
       // row-sharded: a column's statistic spans the row blocks of all ranks (max for Ruiz, sum for Pock-Chambolle)
       if (sharded()) dist->allreduce(scratch_n.data(), n, mode == 0, stream);
       k_apply_scaling_stat<<<grid_m, EW_THREADS, 0, stream>>>(m, Dr.data(), scratch_m.data());
@@ -778,10 +789,15 @@ struct pdlp_solver_t::impl_t {
   void scale_problem()
   {
     nvtx_range_t nvtx_scope("scale_problem");
-    const int wg_m = std::max(1, std::min((m + 7) / 8, sms * 16));
-    const int wg_n = std::max(1, std::min((n + 7) / 8, sms * 16));
-    k_scale_matrix<<<wg_m, 256, 0, stream>>>(m, As.off_ptr(), As.idx_ptr(), As.val.data(), Dr.data(), Dc.data());
-    k_scale_matrix<<<wg_n, 256, 0, stream>>>(n, ATs.off_ptr(), ATs.idx_ptr(), ATs.val.data(), Dc.data(), Dr.data());
+    auto scale = [&](csr_dev_t& M, const double* rs, const double* cs) {
+      const int w    = row_group_width(M);
+      const int grid = std::max(1, std::min((int)(((long long)M.rows * w + 255) / 256), sms * 16));
+#define CUOPT_SCALE(W) k_scale_matrix<W><<<grid, 256, 0, stream>>>(M.rows, M.off_ptr(), M.idx_ptr(), M.val.data(), rs, cs)
+      if (w == 4) CUOPT_SCALE(4); else if (w == 8) CUOPT_SCALE(8); else if (w == 16) CUOPT_SCALE(16); else CUOPT_SCALE(32);
+#undef CUOPT_SCALE
+    };
+    scale(As, Dr.data(), Dc.data());
+    scale(ATs, Dc.data(), Dr.data());
     k_scale_vector<<<grid_n, EW_THREADS, 0, stream>>>(n, cs.data(), Dc.data(), 0);
     k_scale_vector<<<grid_n, EW_THREADS, 0, stream>>>(n, ls.data(), Dc.data(), 1);
     k_scale_vector<<<grid_n, EW_THREADS, 0, stream>>>(n, us.data(), Dc.data(), 1);
@@ -1034,18 +1050,25 @@ struct pdlp_solver_t::impl_t {
       sync();
       build_bicsr(Ahot, hoff, stream, sms);
     }
+    trace.mark("  gather transport: packed A_g (positions, renumbered indices, BICSR)");
     build_gather_blocks(Ahot, blkA, t_m);
+    trace.mark("  gather transport: gather blocks of the packed A_g");
     exchange_positions(posX, slice_j0, nslice, sendX);
+    trace.mark("  gather transport: xbar send tables from the peers");
     // y' side: the constraint rows this rank's rows of the global A^T touch
     std::vector<int> hoff = build_slice_transpose();
+    trace.mark("  gather transport: rows J_g of the global A^T from the peers");
     cntY = packed_positions(m_total, m_total, ATslice.nnz, ATslice.idx.data(), posY);
     if (ATslice.nnz > 0)
       k_remap_indices<<<ew_grid(ATslice.nnz, sms), EW_THREADS, 0, stream>>>(ATslice.nnz, ATslice.idx.data(), posY.data(),
                                                                             ATslice.idx.data());
     ATslice.cols = std::max(cntY, 1);
     build_bicsr(ATslice, hoff, stream, sms);
+    trace.mark("  gather transport: packed A^T slice (positions, renumbered indices, BICSR)");
     build_gather_blocks(ATslice, blkATslice, t_slice);
+    trace.mark("  gather transport: gather blocks of the A^T slice");
     exchange_positions(posY, row0[dist->rank], m, sendY);
+    trace.mark("  gather transport: y' send tables from the peers");
     check_launch();
     sync();
   }
