@@ -8,6 +8,8 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -43,8 +45,87 @@ inline double alloc_clock()
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// Device array with value semantics disabled; memory comes straight from cudaMalloc
-// (one allocation per vector, sized once per solve: no pool needed at 180 GB HBM).
+// Freed device blocks are kept (per device, up to a cap) and handed out again to a request of exactly the same size: a solve
+// allocates ~100 arrays, and at configs[3] their cudaFree calls alone took 0.5-0.7 s of a 3.5 s end-to-end solve (7 ms each for
+// multi-hundred-MB blocks, CUOPT_B200_TRACE=1) — the reference sits on RMM's pool for the same reason.  A block enters the cache
+// only after a cudaDeviceSynchronize (the guarantee cudaFree gave: nothing still uses it); over the cap the oldest blocks go back
+// to the driver; an out-of-memory cudaMalloc flushes the cache and retries.  CUOPT_B200_DEVICE_CACHE_MB=0 turns it off.
+class device_block_cache_t {
+ public:
+  static device_block_cache_t& get()
+  {
+    static device_block_cache_t* c = new device_block_cache_t;  // never destroyed: the CUDA context may be gone at exit
+    return *c;
+  }
+  void* take(size_t bytes)
+  {
+    if (cap_ == 0) return nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu_);
+    for (size_t i = blocks_.size(); i-- > 0;)
+      if (blocks_[i].bytes == bytes && blocks_[i].dev == dev) {
+        void* p = blocks_[i].p;
+        cached_ -= bytes;
+        blocks_.erase(blocks_.begin() + (long)i);
+        return p;
+      }
+    return nullptr;
+  }
+  void give(void* p, size_t bytes)
+  {
+    if (cap_ == 0 || bytes > cap_) {
+      cudaFree(p);
+      return;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> g(mu_);
+    blocks_.push_back({p, bytes, dev});
+    cached_ += bytes;
+    size_t first_kept = 0;
+    while (cached_ > cap_ && first_kept < blocks_.size()) {  // oldest first; only blocks of the current device can be freed here
+      if (blocks_[first_kept].dev == dev) {
+        cudaFree(blocks_[first_kept].p);
+        cached_ -= blocks_[first_kept].bytes;
+        blocks_.erase(blocks_.begin() + (long)first_kept);
+      } else {
+        ++first_kept;
+      }
+    }
+  }
+  void flush()
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu_);
+    for (size_t i = blocks_.size(); i-- > 0;)
+      if (blocks_[i].dev == dev) {
+        cudaFree(blocks_[i].p);
+        cached_ -= blocks_[i].bytes;
+        blocks_.erase(blocks_.begin() + (long)i);
+      }
+  }
+
+ private:
+  struct block_t {
+    void* p;
+    size_t bytes;
+    int dev;
+  };
+  device_block_cache_t()
+  {
+    cap_ = size_t(48) << 30;
+    if (const char* e = std::getenv("CUOPT_B200_DEVICE_CACHE_MB")) cap_ = (size_t)std::strtoull(e, nullptr, 10) << 20;
+  }
+  std::mutex mu_;
+  std::vector<block_t> blocks_;
+  size_t cached_ = 0, cap_ = 0;
+};
+
+// Device array with value semantics disabled; one allocation per vector, sized once per solve, taken from / returned to the
+// block cache above.
 template <typename T>
 class dvec {
  public:
@@ -69,7 +150,18 @@ class dvec {
     if (n + slack) {
       alloc_stats_t& as = alloc_stats();
       const double t0   = as.on ? alloc_clock() : 0.0;
-      CUOPT_CUDA_TRY(cudaMalloc(&p_, (n + slack) * sizeof(T)));
+      const size_t bytes = (n + slack) * sizeof(T);
+      void* raw          = device_block_cache_t::get().take(bytes);
+      if (raw == nullptr) {
+        cudaError_t err = cudaMalloc(&raw, bytes);
+        if (err == cudaErrorMemoryAllocation) {  // give the cached blocks back and try once more
+          cudaGetLastError();
+          device_block_cache_t::get().flush();
+          err = cudaMalloc(&raw, bytes);
+        }
+        CUOPT_CUDA_TRY(err);
+      }
+      p_ = static_cast<T*>(raw);
       if (as.on) {
         as.malloc_s += alloc_clock() - t0;
         as.n_malloc += 1;
@@ -83,7 +175,7 @@ class dvec {
     if (p_) {
       alloc_stats_t& as = alloc_stats();
       const double t0   = as.on ? alloc_clock() : 0.0;
-      cudaFree(p_);
+      device_block_cache_t::get().give(p_, (n_ + slack_) * sizeof(T));
       if (as.on) {
         as.free_s += alloc_clock() - t0;
         as.n_free += 1;

@@ -148,9 +148,11 @@ __device__ __forceinline__ void pdhg_step_rule(pdhg_ctl_t* ctl, double interacti
 // ---- multi-GPU peer transport primitives (used by the column-sliced attempt further down) ----
 constexpr int DIST_MAX_PEERS        = 8;
 constexpr int DIST_FLAG_XBAR        = 0 * DIST_MAX_PEERS;  // flags[slot + g]: rank g's contribution has landed
-constexpr int DIST_FLAG_PARTIAL     = 1 * DIST_MAX_PEERS;
+constexpr int DIST_FLAG_PARTIAL     = 1 * DIST_MAX_PEERS;  // partial A_g^T y' (p2p transport) / first half of y' (gather transport)
 constexpr int DIST_FLAG_SCALARS     = 2 * DIST_MAX_PEERS;
-constexpr int DIST_FLAG_COUNT       = 3 * DIST_MAX_PEERS;
+constexpr int DIST_FLAG_XBAR_B      = 3 * DIST_MAX_PEERS;  // gather transport: second half of rank g's xbar entries
+constexpr int DIST_FLAG_Y_B         = 4 * DIST_MAX_PEERS;  // gather transport: second half of rank g's y' entries
+constexpr int DIST_FLAG_COUNT       = 5 * DIST_MAX_PEERS;
 constexpr long long DIST_SPIN_LIMIT = 20000000000LL;  // ~10 s of SM clocks, then trap instead of hanging the box
 struct peer_ptrs_t {
   double* p[DIST_MAX_PEERS];
@@ -181,8 +183,9 @@ __device__ __forceinline__ void peer_wait(const unsigned long long* flags, int c
   __syncthreads();
 }
 // whole CTA, after its last peer store: the last CTA of the grid raises flag `index` on every rank
+// index2 >= 0: a second flag raised together with the first (a producer that delivers both halves at once)
 __device__ __forceinline__ void peer_signal_grid_done(unsigned* ticket, const peer_flags_t& flags, int world, int index,
-                                                      unsigned long long epoch)
+                                                      unsigned long long epoch, int index2 = -1)
 {
   __threadfence_system();
   __syncthreads();
@@ -193,7 +196,10 @@ __device__ __forceinline__ void peer_signal_grid_done(unsigned* ticket, const pe
   __threadfence_system();
 #pragma unroll
   for (int r = 0; r < DIST_MAX_PEERS; ++r)
-    if (r < world) st_release_sys(flags.p[r] + index, epoch);
+    if (r < world) {
+      st_release_sys(flags.p[r] + index, epoch);
+      if (index2 >= 0) st_release_sys(flags.p[r] + index2, epoch);
+    }
 }
 
 // =============================================================================================
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(BICSR_THREADS, bicsr_min_ctas(NPRE)) k_dual_st
   spmv_bicsr_rows<payload_t, INIT, NPRE>(A, xbar, rows[threadIdx.x >> 5], pre_op, row_op, pol.keep);
   const double tot = block_reduce(dy2, red);
   if (threadIdx.x == 0) part_dy2[blockIdx.x] = tot;
-  if constexpr (BCAST) peer_signal_grid_done(&ctl->ticket[2], flags, world, DIST_FLAG_PARTIAL + rank, epoch);
+  if constexpr (BCAST) peer_signal_grid_done(&ctl->ticket[2], flags, world, DIST_FLAG_PARTIAL + rank, epoch, DIST_FLAG_Y_B + rank);
 }
 
 // =============================================================================================
@@ -495,12 +501,123 @@ __global__ void __launch_bounds__(EW_THREADS) k_fill_int(int n, int* __restrict_
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = value;
 }
-// pos[j] = slot of entry j in the packed buffer, -1 when it is not needed (scan = exclusive sum of flag)
-__global__ void __launch_bounds__(EW_THREADS) k_packed_positions(int n, const int* __restrict__ flag, const int* __restrict__ scan,
-                                                                 int* __restrict__ pos)
+// Two halves.  The packed buffer of a rank holds first the needed entries that lie in the FIRST half of their owner's slice
+// (slots [0, count A)), then, from slot W on, those of the second halves: the column blocks of the gather-blocked products
+// are cut at W, so the pass over block 0 needs only the first halves — which the owners send first — and runs while the
+// second halves are still on the wire.  owner h holds entries [start[h], start[h + 1]), its first half is the first half[h].
+struct half_map_t {
+  int start[DIST_MAX_PEERS + 1];
+  int half[DIST_MAX_PEERS];
+  int world;
+};
+__global__ void __launch_bounds__(EW_THREADS) k_half_flags(int n, const int* __restrict__ needed, half_map_t hm,
+                                                           int* __restrict__ flag_a, int* __restrict__ flag_b)
 {
   const int stride = gridDim.x * blockDim.x;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) pos[j] = flag[j] ? scan[j] : -1;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    int h = 0;
+#pragma unroll
+    for (int r = 1; r < DIST_MAX_PEERS; ++r)
+      if (r < hm.world && j >= hm.start[r]) h = r;
+    const bool first = (j - hm.start[h]) < hm.half[h];
+    const int need   = needed[j];
+    flag_a[j]        = (need && first) ? 1 : 0;
+    flag_b[j]        = (need && !first) ? 1 : 0;
+  }
+}
+// pos[j] = slot of entry j in the packed buffer, -1 when it is not needed (scan_* = exclusive sums of flag_*)
+__global__ void __launch_bounds__(EW_THREADS) k_packed_positions(int n, const int* __restrict__ flag_a, const int* __restrict__ scan_a,
+                                                                 const int* __restrict__ flag_b, const int* __restrict__ scan_b,
+                                                                 int second_half_base, int* __restrict__ pos)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+    pos[j] = flag_a[j] ? scan_a[j] : flag_b[j] ? second_half_base + scan_b[j] : -1;
+}
+// sender side: list of the local entries a destination reads, ascending (flag = its slot table >= 0, scan = exclusive sum)
+__global__ void __launch_bounds__(EW_THREADS) k_flag_nonnegative(int n, const int* __restrict__ v, int* __restrict__ flag)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) flag[i] = v[i] >= 0 ? 1 : 0;
+}
+__global__ void __launch_bounds__(EW_THREADS) k_fill_list(int n, const int* __restrict__ flag, const int* __restrict__ scan,
+                                                          int* __restrict__ list)
+{
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (flag[i]) list[scan[i]] = i;
+}
+
+// The exchange itself, as its own kernel on the communication stream (it overlaps the first column-block pass of the
+// consumer, see pdlp_solver.cu enqueue_gather_attempt): for every destination rank, its slots in DESTINATION order — thread k
+// stores v[list[k]] into slot base + k, warps aligned to 256-byte segments of the destination, so the NVLink stores are
+// full contiguous lines (stores issued in SOURCE order by the producing kernel hit every destination with ragged ~20-of-32
+// lane runs and reached half the link rate: profiles/r2/dist_slot_trace_c4_n8_fused_stores.txt).  First halves of all
+// destinations, flag A, second halves, flag B.  Destinations are visited starting after the sender's own rank.
+constexpr int SEND_UNROLL = 8;
+struct send_plan_t {
+  int count_a[DIST_MAX_PEERS];  // entries of the first half that destination r reads
+  int count[DIST_MAX_PEERS];    // all entries it reads (the list holds the first-half ones first)
+};
+__global__ void __launch_bounds__(EW_THREADS, 8) k_send_packed(const pdhg_ctl_t* __restrict__ ctl,
+                                                               const double* __restrict__ v0,
+                                                               const double* __restrict__ v1,
+                                                               int pick_candidate,  // 1: v = parity ? v0 : v1 (the candidate y')
+                                                               const int* __restrict__ list,  // [world][stride]
+                                                               const int* __restrict__ slot,  // [world][stride]: slot of entry i at rank r
+                                                               int stride,
+                                                               send_plan_t plan,
+                                                               peer_ptrs_t peers,
+                                                               peer_flags_t flags,
+                                                               int world,
+                                                               int rank,
+                                                               int flag_a,
+                                                               int flag_b,
+                                                               unsigned* __restrict__ tickets)
+{
+  if (!ctl->active) return;
+  const unsigned long long epoch = (unsigned long long)ctl->attempts + 1ull;
+  const double* v   = pick_candidate ? (ctl->parity ? v0 : v1) : v0;
+  const int gstride = gridDim.x * blockDim.x;
+  const int gtid    = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int part = 0; part < 2; ++part) {
+    for (int d = 0; d < world; ++d) {
+      int r = rank + 1 + d;
+      if (r >= world) r -= world;
+      int lo = 0, hi = 0;
+      double* dst = peers.p[0];
+#pragma unroll
+      for (int q = 0; q < DIST_MAX_PEERS; ++q)
+        if (q == r) {
+          lo  = part ? plan.count_a[q] : 0;
+          hi  = part ? plan.count[q] : plan.count_a[q];
+          dst = peers.p[q];
+        }
+      if (hi <= lo) continue;
+      const int* lst  = list + (size_t)r * stride;
+      const int* slt  = slot + (size_t)r * stride;
+      const int base  = __ldg(slt + __ldg(lst + lo));  // slots of a half are consecutive from here
+      const int shift = base & 31;
+      const int total = hi - lo + shift;
+      // few CTAs (the SpMV kernels keep almost the whole GPU): SEND_UNROLL independent list -> value chains per thread
+      for (int t0 = gtid; t0 < total; t0 += gstride * SEND_UNROLL) {
+        int src[SEND_UNROLL];
+        double val[SEND_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SEND_UNROLL; ++u) {
+          const int k = t0 + u * gstride - shift;
+          src[u]      = (k >= 0 && k < hi - lo) ? __ldg(lst + lo + k) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < SEND_UNROLL; ++u) val[u] = src[u] >= 0 ? v[src[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < SEND_UNROLL; ++u)
+          if (src[u] >= 0) dst[base + t0 + u * gstride - shift] = val[u];
+      }
+    }
+    peer_signal_grid_done(tickets + part, flags, world, (part ? flag_b : flag_a) + rank, epoch);
+    __syncthreads();
+  }
 }
 __global__ void __launch_bounds__(EW_THREADS) k_remap_indices(int nnz, const int* __restrict__ idx_in, const int* __restrict__ pos,
                                                               int* __restrict__ idx_out)
@@ -641,7 +758,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_primal_step_bcast(pdhg_ctl_t* __
         if (r < world) xbar_peers.p[r][j] = xb;
     }
   }
-  peer_signal_grid_done(&ctl->ticket[1], flags, world, DIST_FLAG_XBAR + rank, epoch);
+  peer_signal_grid_done(&ctl->ticket[1], flags, world, DIST_FLAG_XBAR + rank, epoch, send ? DIST_FLAG_XBAR_B + rank : -1);
 }
 
 // K3p with the reduce-scatter fused in: column j's partial goes straight to its owner's staging row of this rank;

@@ -348,9 +348,22 @@ struct pdlp_solver_t::impl_t {
   // packed exchange: Ahot = the scaled A_g with column indices renumbered to the entries of xbar this rank reads; sendX / sendY
   // = per destination rank, where each of MY xbar / y' entries lives in ITS packed buffer (-1: it never reads that entry)
   csr_dev_t Ahot;
-  dvec<int> sendX, sendY;
-  int cntX = 0, cntY = 0;
-  bool dist_pack = true;  // CUOPT_B200_DIST_PACK=0: identity packing (everything travels), for comparison
+  dvec<int> sendX, sendY;    // [world][stride]: slot of my entry i in rank r's packed buffer, -1 if r never reads it
+  dvec<int> listX, listY;    // [world][stride]: my entries rank r reads, ascending (first-half entries first)
+  send_plan_t planX{}, planY{};
+  dvec<double> xloc;         // this rank's slice of xbar before it is sent
+  int cntX = 0, cntY = 0;    // packed lengths (second half starts at half the length)
+  bool dist_pack = true;     // CUOPT_B200_DIST_PACK=0: identity packing (everything travels), for comparison
+  // How the packed entries travel.  "fused" (default): the producing kernels (K1, K2) issue the peer stores themselves, in
+  // source order, overlapped with their own work: 588 us per attempt at configs[3] on 2 GPUs, 363 us on 8 (measured).
+  // "kernel" (CUOPT_B200_DIST_SEND=kernel): k_send_packed on a second stream, destination order (full 256-byte lines), halves
+  // pipelined with the consumer's column blocks.  Measured on 2 GPUs only: 790 us per attempt — the SpMV kernels lose the CTA
+  // slots reserved for the send kernel and the first half's wire time is exposed; the 8-GPU regime it was written for (wire-
+  // bound attempts, source-order stores at half the link rate) could not be measured inside this round's GPU budget.
+  bool dist_send_kernel = false;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int grid_send = 1, send_slots = 0;  // SpMV CTA slots left to the send kernel (default: one per SM); CUOPT_B200_DIST_SEND_SLOTS
   const csr_dev_t& hot_A() const { return (dist != nullptr && dist->world > 1 && dist_mode == DIST_GATHER) ? Ahot : As; }
   // CUOPT_B200_DIST_TRACE=1: CUDA-event time of every kernel slot of the sharded attempt (waiting for the peers' flags
   // included), printed per rank when the solver goes away.  Turns the CUDA graphs off and synchronises once per attempt.
@@ -465,6 +478,9 @@ struct pdlp_solver_t::impl_t {
                    "(each slot includes the wait for the peers' flags)\n", dist->rank, dist->world, dist_mode, tr_count,
                    1e3 * tr_acc[0] / tr_count, 1e3 * tr_acc[1] / tr_count, 1e3 * tr_acc[2] / tr_count, 1e3 * tr_acc[3] / tr_count);
     for (auto& e : tr_ev) if (e) cudaEventDestroy(e);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
     close_peer_memory(false);
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
     if (ev_a) cudaEventDestroy(ev_a);
@@ -478,7 +494,12 @@ struct pdlp_solver_t::impl_t {
   // one wave of resident CTAs, or fewer when the matrix has fewer blocks than that (8 warps = 8 blocks per CTA)
   int spmv_grid(const csr_dev_t& M, int npre = 1) const
   {
-    return std::max(1, std::min((M.n_blk() + BICSR_WARPS - 1) / BICSR_WARPS, sms * (npre > 1 ? occ_spmv2 : occ_spmv)));
+    // gather transport: a consumer may spin on flags the send kernel of THIS rank still has to raise, so that kernel must
+    // always find room beside a full wave of SpMV CTAs: send_slots CTA slots stay free (wherever the scheduler leaves them: each
+    // holds >= 16 K registers = 2 send CTAs of 256 threads x 28 registers, and the send grid is 2 x send_slots CTAs)
+    const int reserve = (dist != nullptr && dist->world > 1 && dist_mode == DIST_GATHER && dist_send_kernel) ? send_slots : 0;
+    const int wave    = std::max(1, sms * (npre > 1 ? occ_spmv2 : occ_spmv) - reserve);
+    return std::max(1, std::min((M.n_blk() + BICSR_WARPS - 1) / BICSR_WARPS, wave));
   }
   // payload row groups the fused kernels fetch ahead (spmv_bicsr.cuh): 2 when the blocks hold clearly more than 32 rows
   int fused_npre(const csr_dev_t& M) const
@@ -593,7 +614,11 @@ struct pdlp_solver_t::impl_t {
       ybuf[b].resize(m); ybuf[b].zero(stream);
       atybuf[b].resize(n, pad); atybuf[b].zero(stream);
     }
-    for (dvec<double>* v : {&xbar, &sum_x}) { v->resize(n, pad); v->zero(stream); }
+    // xbar doubles as the packed receive buffer of the gather transport: two halves, each rounded up to 32 slots
+    xbar.resize(n, pad + (sharded() ? 64 * (size_t)dist->world + 64 : 0));
+    xbar.zero(stream);
+    sum_x.resize(n, pad);
+    sum_x.zero(stream);
     for (dvec<double>* v : {&x_avg, &x_lr, &rc_cur, &rc_avg, &scratch_n}) { v->resize(n); v->zero(stream); }
     for (dvec<double>* v : {&sum_y, &y_avg, &y_lr, &scratch_m}) { v->resize(m); v->zero(stream); }
     Dr.resize(m);
@@ -649,7 +674,7 @@ struct pdlp_solver_t::impl_t {
     part_misc.resize(2 * (size_t)std::max(grid_misc, ew_grid(nnz, sms)));
     d_scalar.resize(12);
     if (sharded()) setup_transport();
-    d_ticket.resize(4);
+    d_ticket.resize(8);
     d_ticket.zero(stream);
     d_ctl.resize(1);
     d_ctl.zero(stream);
@@ -693,7 +718,13 @@ struct pdlp_solver_t::impl_t {
     if (dist_mode == DIST_NCCL_SLICES) { rs_buf.resize(nslice); rs_buf.zero(stream); }
     if (peer_transport()) {
       if (dist_mode == DIST_P2P) stage.resize((size_t)nslice * dist->world);
-      else { stage.resize(32); yfull.resize((size_t)std::max(m_total, 32)); yfull.zero(stream); }
+      else {
+        stage.resize(32);
+        yfull.resize((size_t)m_total + 64 * (size_t)dist->world + 64);
+        yfull.zero(stream);
+        xloc.resize((size_t)std::max(nslice, 32));
+        xloc.zero(stream);
+      }
       stage.zero(stream);
       d_flags.resize(DIST_FLAG_COUNT);
       d_flags.zero(stream);
@@ -722,6 +753,15 @@ struct pdlp_solver_t::impl_t {
     }
     if (const char* e = std::getenv("CUOPT_B200_DIST_TRACE")) dist_trace = e[0] == '1';
     if (const char* e = std::getenv("CUOPT_B200_DIST_PACK")) dist_pack = e[0] != '0';
+    if (const char* e = std::getenv("CUOPT_B200_DIST_SEND")) dist_send_kernel = std::string(e) == "kernel";
+    if (dist_mode == DIST_GATHER) {
+      CUOPT_CUDA_TRY(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+      CUOPT_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      CUOPT_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      send_slots = sms;  // measured on 2 GPUs: 32 slots / 64 send CTAs cannot feed the link (880 us per attempt against 790)
+      if (const char* e = std::getenv("CUOPT_B200_DIST_SEND_SLOTS")) send_slots = std::max(1, std::min(std::atoi(e), sms));
+      grid_send = 2 * send_slots;
+    }
     if (dist_trace) {
       use_graphs = false;
       for (auto& e : tr_ev) CUOPT_CUDA_TRY(cudaEventCreate(&e));
@@ -995,25 +1035,54 @@ struct pdlp_solver_t::impl_t {
     return hoff;
   }
 
-  // Which of `count` entries occur among `nnz` indices -> pos[j] = slot in the packed buffer or -1 (identity when packing is
-  // off); returns the packed length.  pos has `padded` >= count entries (the pad is -1).
-  int packed_positions(int count, int padded, int nnz, const int* idx, dvec<int>& pos)
+  // Which of `count` entries occur among `nnz` indices -> pos[j] = slot in the packed buffer or -1 (every entry when packing
+  // is off).  The needed entries of the first halves (hm) fill slots [0, W), those of the second halves [W, 2 W); returns W
+  // (a multiple of 32).  pos has `padded` >= count entries (the pad is -1).
+  int packed_positions(int count, int padded, int nnz, const int* idx, const half_map_t& hm, dvec<int>& pos)
   {
-    dvec<int> flag((size_t)padded + 1), scan((size_t)padded + 1);
-    flag.zero(stream);
+    const size_t len = (size_t)padded + 1;
+    dvec<int> need(len), fa(len), fb(len), sa(len), sb(len);
+    need.zero(stream);
     if (dist_pack) {
-      if (nnz > 0) k_mark_indices<<<ew_grid(nnz, sms), EW_THREADS, 0, stream>>>(nnz, idx, flag.data());
+      if (nnz > 0) k_mark_indices<<<ew_grid(nnz, sms), EW_THREADS, 0, stream>>>(nnz, idx, need.data());
     } else if (count > 0) {
-      k_fill_int<<<ew_grid(count, sms), EW_THREADS, 0, stream>>>(count, flag.data(), 1);
+      k_fill_int<<<ew_grid(count, sms), EW_THREADS, 0, stream>>>(count, need.data(), 1);
     }
-    exclusive_sum_int(padded + 1, flag.data(), scan.data(), stream);
+    k_half_flags<<<ew_grid((int)len, sms), EW_THREADS, 0, stream>>>((int)len, need.data(), hm, fa.data(), fb.data());
+    exclusive_sum_int((int)len, fa.data(), sa.data(), stream);
+    exclusive_sum_int((int)len, fb.data(), sb.data(), stream);
+    int tot[2] = {0, 0};
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(&tot[0], sa.data() + padded, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUOPT_CUDA_TRY(cudaMemcpyAsync(&tot[1], sb.data() + padded, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    sync();
+    const int W = (std::max({tot[0], tot[1], 1}) + 31) & ~31;
     pos.resize((size_t)std::max(padded, 1));
-    if (padded > 0) k_packed_positions<<<ew_grid(padded, sms), EW_THREADS, 0, stream>>>(padded, flag.data(), scan.data(), pos.data());
-    int total = 0;
-    CUOPT_CUDA_TRY(cudaMemcpyAsync(&total, scan.data() + padded, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (padded > 0)
+      k_packed_positions<<<ew_grid(padded, sms), EW_THREADS, 0, stream>>>(padded, fa.data(), sa.data(), fb.data(), sb.data(), W,
+                                                                        pos.data());
     check_launch();
     sync();
-    return total;
+    return W;
+  }
+  // Sender side: from the slot table of every destination (tbl[r * count + i]) the ascending list of my entries it reads and
+  // how many of them lie below `half` (they are sent, and flagged, first).
+  void build_send_lists(const dvec<int>& tbl, int count, int half, dvec<int>& list, send_plan_t& plan)
+  {
+    const int G = dist->world;
+    plan        = send_plan_t{};
+    list.resize((size_t)std::max(count, 1) * G);
+    if (count <= 0) return;
+    dvec<int> flag((size_t)count + 1), scan((size_t)count + 1);
+    for (int r = 0; r < G; ++r) {
+      flag.zero(stream);
+      k_flag_nonnegative<<<ew_grid(count, sms), EW_THREADS, 0, stream>>>(count, tbl.data() + (size_t)r * count, flag.data());
+      exclusive_sum_int(count + 1, flag.data(), scan.data(), stream);
+      k_fill_list<<<ew_grid(count, sms), EW_THREADS, 0, stream>>>(count, flag.data(), scan.data(), list.data() + (size_t)r * count);
+      CUOPT_CUDA_TRY(cudaMemcpyAsync(&plan.count_a[r], scan.data() + std::min(half, count), sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CUOPT_CUDA_TRY(cudaMemcpyAsync(&plan.count[r], scan.data() + count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      check_launch();
+      sync();
+    }
   }
   // every rank's pos array (same length everywhere) -> mine[g * count + i] = peer g's pos[first + i]  (collective)
   void exchange_positions(dvec<int>& pos, int first, int count, dvec<int>& mine)
@@ -1033,56 +1102,80 @@ struct pdlp_solver_t::impl_t {
   }
   void build_gather_transport()
   {
-    // xbar side: the columns this rank's rows of A touch
+    const int G = dist->world, rk = dist->rank;
+    // xbar side: the columns this rank's rows of A touch; owner h holds columns [h nslice, (h + 1) nslice)
+    half_map_t hx{}, hy{};
+    hx.world = hy.world = G;
+    for (int h = 0; h < G; ++h) {
+      hx.start[h] = h * nslice;
+      hx.half[h]  = nslice / 2;
+      hy.start[h] = row0[h];
+      hy.half[h]  = (row0[h + 1] - row0[h] + 1) / 2;
+    }
+    for (int h = G; h <= DIST_MAX_PEERS; ++h) { hx.start[h] = n_pad; hy.start[h] = m_total; }
     dvec<int> posX, posY;
-    cntX = packed_positions(n, n_pad, A.nnz, A.idx.data(), posX);
+    const int WX = packed_positions(n, n_pad, A.nnz, A.idx.data(), hx, posX);
+    cntX         = 2 * WX;
+    if ((size_t)cntX > (size_t)n_pad + 64 * (size_t)G + 64) throw lp_error(error_type_t::RuntimeError, "gather transport: packed xbar exceeds its buffer");
     Ahot      = csr_dev_t{};
     Ahot.rows = m;
-    Ahot.cols = std::max(cntX, 1);
+    Ahot.cols = cntX;
     Ahot.nnz  = A.nnz;
     Ahot.off.copy_from(A.off, stream);
     Ahot.idx.resize((size_t)std::max(A.nnz, 1));
     if (A.nnz > 0) k_remap_indices<<<ew_grid(A.nnz, sms), EW_THREADS, 0, stream>>>(A.nnz, A.idx.data(), posX.data(), Ahot.idx.data());
     Ahot.val.copy_from(As.val, stream);
-    {
+    trace.mark("  gather transport: packed A_g (positions, renumbered indices)");
+    build_gather_blocks(Ahot, blkA, t_m, WX);  // block 0 = first halves, block 1 = second halves
+    if (!blkA.on()) {
       std::vector<int> hoff((size_t)m + 1);
       A.off.download(hoff.data(), stream);
       sync();
       build_bicsr(Ahot, hoff, stream, sms);
     }
-    trace.mark("  gather transport: packed A_g (positions, renumbered indices, BICSR)");
-    build_gather_blocks(Ahot, blkA, t_m);
-    trace.mark("  gather transport: gather blocks of the packed A_g");
-    exchange_positions(posX, slice_j0, nslice, sendX);
-    trace.mark("  gather transport: xbar send tables from the peers");
+    trace.mark("  gather transport: column blocks of the packed A_g");
+    exchange_positions(posX, rk * nslice, nslice, sendX);
+    build_send_lists(sendX, nslice, hx.half[rk], listX, planX);
+    trace.mark("  gather transport: xbar send tables and lists");
     // y' side: the constraint rows this rank's rows of the global A^T touch
     std::vector<int> hoff = build_slice_transpose();
     trace.mark("  gather transport: rows J_g of the global A^T from the peers");
-    cntY = packed_positions(m_total, m_total, ATslice.nnz, ATslice.idx.data(), posY);
+    const int WY = packed_positions(m_total, m_total, ATslice.nnz, ATslice.idx.data(), hy, posY);
+    cntY         = 2 * WY;
+    if ((size_t)cntY > yfull.size()) throw lp_error(error_type_t::RuntimeError, "gather transport: packed y' exceeds its buffer");
     if (ATslice.nnz > 0)
       k_remap_indices<<<ew_grid(ATslice.nnz, sms), EW_THREADS, 0, stream>>>(ATslice.nnz, ATslice.idx.data(), posY.data(),
                                                                             ATslice.idx.data());
-    ATslice.cols = std::max(cntY, 1);
-    build_bicsr(ATslice, hoff, stream, sms);
-    trace.mark("  gather transport: packed A^T slice (positions, renumbered indices, BICSR)");
-    build_gather_blocks(ATslice, blkATslice, t_slice);
-    trace.mark("  gather transport: gather blocks of the A^T slice");
-    exchange_positions(posY, row0[dist->rank], m, sendY);
-    trace.mark("  gather transport: y' send tables from the peers");
+    ATslice.cols = cntY;
+    trace.mark("  gather transport: packed A^T slice (positions, renumbered indices)");
+    build_gather_blocks(ATslice, blkATslice, t_slice, WY);
+    if (!blkATslice.on()) build_bicsr(ATslice, hoff, stream, sms);
+    trace.mark("  gather transport: column blocks of the A^T slice");
+    exchange_positions(posY, row0[rk], m, sendY);
+    build_send_lists(sendY, m, hy.half[rk], listY, planY);
+    trace.mark("  gather transport: y' send tables and lists");
     check_launch();
     sync();
   }
 
   // ------------------------------------------------------------------------------ PDHG batches
   // Cuts the scaled matrix M into column blocks (device, stable) when the vector it gathers from exceeds the block size.
-  void build_gather_blocks(const csr_dev_t& M, gather_blocks_t& g, dvec<double>& t)
+  // forced_width > 0 (gather transport): exactly two blocks, cut at that column, whatever the size of the gathered vector
+  void build_gather_blocks(const csr_dev_t& M, gather_blocks_t& g, dvec<double>& t, int forced_width = 0)
   {
     g = gather_blocks_t{};
     const size_t bytes = (size_t)M.cols * sizeof(double);
-    if (gather_block_bytes == 0 || bytes <= gather_block_bytes + gather_block_bytes / 2 || M.nnz == 0) return;
-    int B     = (int)std::min<size_t>(16, (bytes + gather_block_bytes - 1) / gather_block_bytes);
-    g.width   = (((M.cols + B - 1) / B) + 31) & ~31;
-    B         = (M.cols + g.width - 1) / g.width;
+    int B              = 1;
+    if (forced_width > 0) {
+      if (M.nnz == 0 || M.rows == 0) return;
+      g.width = forced_width;
+      B       = 2;
+    } else {
+      if (gather_block_bytes == 0 || bytes <= gather_block_bytes + gather_block_bytes / 2 || M.nnz == 0) return;
+      B       = (int)std::min<size_t>(16, (bytes + gather_block_bytes - 1) / gather_block_bytes);
+      g.width = (((M.cols + B - 1) / B) + 31) & ~31;
+      B       = (M.cols + g.width - 1) / g.width;
+    }
     if (B <= 1) return;
     g.B = B;
     g.blk.resize(B);
@@ -1129,14 +1222,16 @@ struct pdlp_solver_t::impl_t {
   // K2: one fused kernel; with gather blocking (B - 1) payload-free passes over the first column blocks, then the fused kernel
   // on the last block continuing their running sum.  wait_flags: peer transport (xbar slices of the peers)
   // bcast: gather transport, the fused kernel also stores y' into every rank's all-gathered y' buffer
-  void enqueue_k2(const unsigned long long* wait_flags, int n_wait, bool bcast = false)
+  // wait_flags_b (gather transport): the second halves' flags, awaited by the kernel of the LAST column block
+  void enqueue_k2(const unsigned long long* wait_flags, int n_wait, bool bcast = false,
+                  const unsigned long long* wait_flags_b = nullptr)
   {
     const bool blocked  = blkA.on();
     const csr_dev_t& L  = blocked ? blkA.blk[blkA.B - 1] : hot_A();
     const int npre      = fused_npre(L);
     const int grid      = spmv_grid(L, npre);
     const double* t     = blocked ? t_m.data() : nullptr;
-    const unsigned long long* wf = blocked ? nullptr : wait_flags;
+    const unsigned long long* wf = wait_flags_b ? wait_flags_b : (blocked ? nullptr : wait_flags);
     if (blocked) launch_block_passes(blkA, blkA.B - 1, xbar.data(), xbar.data(), 0, t_m.data(), wait_flags, n_wait);
 #define CUOPT_K2(INIT, NPRE)                                                                                             \
   k_dual_step<INIT, NPRE><<<grid, BICSR_THREADS, 0, stream>>>(d_ctl.data(), L.view(), xbar.data(), ybuf[0].data(),       \
@@ -1182,7 +1277,7 @@ struct pdlp_solver_t::impl_t {
   {
     const int k2 = blkA.on() ? blkA.B : 1;
     if (!sharded()) return 1 + k2 + (blkAT.on() ? blkAT.B : 1);
-    if (dist_mode == DIST_GATHER) return 1 + k2 + (blkATslice.on() ? blkATslice.B : 1) + 1;
+    if (dist_mode == DIST_GATHER) return 1 + k2 + (blkATslice.on() ? blkATslice.B : 1) + 1 + (dist_send_kernel ? 2 : 0);
     const int k3p = blkAT.on() ? blkAT.B + (dist_mode == DIST_P2P ? 1 : 0) : 1;
     return 1 + k2 + k3p + (dist_mode == DIST_ALLREDUCE ? 2 : 2);
   }
@@ -1209,28 +1304,49 @@ struct pdlp_solver_t::impl_t {
     const int j0 = slice_j0, G = dist->world, rk = dist->rank;
     double *x0 = xbuf[0].data() + j0, *x1 = xbuf[1].data() + j0, *a0 = atybuf[0].data() + j0, *a1 = atybuf[1].data() + j0;
     if (dist_mode == DIST_GATHER) {
+      const unsigned long long* fl = d_flags.data();
       tr_tick(0);
-      k_primal_step_bcast<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, x0, x1, a0, a1, cs.data() + j0,
-                                                                 ls.data() + j0, us.data() + j0, sum_x.data() + j0, p_xbar,
-                                                                 p_flags, G, rk, sendX.data(), nslice);
+      if (dist_send_kernel) {
+        // K1 on the slice, then the xbar exchange on the communication stream: first halves -> flag A, second halves -> flag B
+        k_primal_step<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, x0, x1, a0, a1, cs.data() + j0,
+                                                             ls.data() + j0, us.data() + j0, sum_x.data() + j0, xloc.data());
+        CUOPT_CUDA_TRY(cudaEventRecord(ev_fork, stream));
+        CUOPT_CUDA_TRY(cudaStreamWaitEvent(comm_stream, ev_fork, 0));
+        k_send_packed<<<grid_send, EW_THREADS, 0, comm_stream>>>(d_ctl.data(), xloc.data(), xloc.data(), 0, listX.data(),
+                                                                 sendX.data(), nslice, planX, p_xbar, p_flags, G, rk,
+                                                                 DIST_FLAG_XBAR, DIST_FLAG_XBAR_B, d_ticket.data() + 4);
+      } else {
+        k_primal_step_bcast<<<grid_slice, EW_THREADS, 0, stream>>>(d_ctl.data(), slice_n, x0, x1, a0, a1, cs.data() + j0,
+                                                                   ls.data() + j0, us.data() + j0, sum_x.data() + j0, p_xbar,
+                                                                   p_flags, G, rk, sendX.data(), nslice);
+      }
       tr_tick(1);
-      enqueue_k2(d_flags.data() + DIST_FLAG_XBAR, G, true);
+      // K2: the pass over column block 0 (first halves) runs while the second halves are still on the wire
+      enqueue_k2(fl + DIST_FLAG_XBAR, G, !dist_send_kernel, fl + DIST_FLAG_XBAR_B);
       tr_tick(2);
-      // K3 on this rank's rows of the global A^T, gathering from the all-gathered y' (the first kernel that touches it waits
-      // for the G y' flags); its last CTA sends this rank's three scalars to everyone
+      if (dist_send_kernel) {
+        CUOPT_CUDA_TRY(cudaEventRecord(ev_fork, stream));
+        CUOPT_CUDA_TRY(cudaStreamWaitEvent(comm_stream, ev_fork, 0));
+        k_send_packed<<<grid_send, EW_THREADS, 0, comm_stream>>>(d_ctl.data(), ybuf[0].data(), ybuf[1].data(), 1, listY.data(),
+                                                                 sendY.data(), m, planY, p_yfull, p_flags, G, rk,
+                                                                 DIST_FLAG_PARTIAL, DIST_FLAG_Y_B, d_ticket.data() + 4);
+        CUOPT_CUDA_TRY(cudaEventRecord(ev_join, comm_stream));
+      }
+      // K3 on this rank's rows of the global A^T, gathering from the packed y'; its last CTA sends this rank's three scalars
       const bool blocked = blkATslice.on();
       const csr_dev_t& L = blocked ? blkATslice.blk[blkATslice.B - 1] : ATslice;
       const int grid     = spmv_grid(L, 1);
-      const unsigned long long* yflags = d_flags.data() + DIST_FLAG_PARTIAL;
-      if (blocked) launch_block_passes(blkATslice, blkATslice.B - 1, yfull.data(), yfull.data(), 0, t_slice.data(), yflags, G);
+      if (blocked)
+        launch_block_passes(blkATslice, blkATslice.B - 1, yfull.data(), yfull.data(), 0, t_slice.data(), fl + DIST_FLAG_PARTIAL, G);
 #define CUOPT_K3S(INIT)                                                                                                     \
   k_transpose_step_slice<INIT, 1><<<grid, BICSR_THREADS, 0, stream>>>(                                                      \
     d_ctl.data(), L.view(), yfull.data(), x0, x1, a0, a1, part_k3.data(), part_dy2.data(), n_part_dy2,                      \
-    blocked ? t_slice.data() : nullptr, blocked ? nullptr : yflags, G, p_scal, p_flags, G, rk)
+    blocked ? t_slice.data() : nullptr, fl + DIST_FLAG_Y_B, G, p_scal, p_flags, G, rk)
       if (blocked) CUOPT_K3S(true); else CUOPT_K3S(false);
 #undef CUOPT_K3S
       tr_tick(3);
       k_step_rule_gather<<<1, 32, 0, stream>>>(d_ctl.data(), scal.data(), G, d_flags.data() + DIST_FLAG_SCALARS);
+      if (dist_send_kernel) CUOPT_CUDA_TRY(cudaStreamWaitEvent(stream, ev_join, 0));  // the communication stream joins
       tr_tick(4);
       tr_close(4);
       return;

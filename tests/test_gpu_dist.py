@@ -21,8 +21,10 @@ def _worker(rank, world, port, q, size, extra_cols, tol, mode, transport, block_
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       CUOPT_B200_DIST_MODE=transport.split("-")[0])
-    if transport.endswith("-nopack"):  # gather transport with identity packing: every entry of xbar / y' travels
+    if "-nopack" in transport:  # gather transport with identity packing: every entry of xbar / y' travels
         os.environ["CUOPT_B200_DIST_PACK"] = "0"
+    if "-kernel" in transport:  # gather transport with k_send_packed on the communication stream instead of the fused peer stores
+        os.environ["CUOPT_B200_DIST_SEND"] = "kernel"
     if block_bytes:
         os.environ["CUOPT_B200_GATHER_BLOCK_BYTES"] = str(block_bytes)
     torch.cuda.set_device(rank)
@@ -88,7 +90,7 @@ def _single_gpu(size, tol, mode, iteration_limit=0, nnz_per_row=8, extra_cols=0)
     return lp, one
 
 
-@pytest.mark.parametrize("transport,nnz_per_row", [("gather", 8), ("gather", 2), ("gather-nopack", 2), ("p2p", 8), ("nccl", 8)])
+@pytest.mark.parametrize("transport,nnz_per_row", [("gather", 8), ("gather", 2), ("gather-nopack", 2), ("gather-kernel", 8), ("gather-kernel", 2), ("p2p", 8), ("nccl", 8)])
 def test_sharded_iterates_track_the_single_gpu_iterates(transport, nnz_per_row):
     """The strongest check of a transport: after the SAME number of iterations (no tolerance involved) the sharded solve holds
     the iterate the single GPU holds, element-wise, up to the summation order of the row sums (block cuts of the row blocks
