@@ -139,3 +139,29 @@ def reference_protocol_step_gather(shard, at_slice, rank, world, x_slice, x_next
     for g in range(world):
         tot += table[g]
     return y_next, aty_next_slice, float(tot[0]), float(tot[1]), float(tot[2])
+
+
+# ---- packed exchange of the gather transport, restated in numpy for the CPU tests ---------------------------
+def packed_layout(needed, starts, halves):
+    """What packed_positions (pdlp_solver.cu) builds on the device: `needed` marks the entries of a distributed vector this
+    rank reads, owner h holds entries [starts[h], starts[h + 1]) and its first half is the first halves[h] of them.  The needed
+    entries of the first halves get slots 0, 1, ... in ascending order, those of the second halves W, W + 1, ...
+    (W = the larger count rounded up to 32).  Returns (pos, W): pos[j] = slot of entry j, -1 if never read."""
+    needed = np.asarray(needed, bool)
+    idx = np.arange(len(needed))
+    owner = np.searchsorted(np.asarray(starts)[1:], idx, side="right")
+    owner = np.minimum(owner, len(halves) - 1)
+    first = (idx - np.asarray(starts)[owner]) < np.asarray(halves)[owner]
+    fa, fb = needed & first, needed & ~first
+    W = (max(int(fa.sum()), int(fb.sum()), 1) + 31) & ~31
+    pos = np.full(len(needed), -1, np.int64)
+    pos[fa] = np.arange(int(fa.sum()))
+    pos[fb] = W + np.arange(int(fb.sum()))
+    return pos, W
+
+
+def send_list(slots_at_destination, half):
+    """Sender side (build_send_lists): from the destination's slots of MY entries (-1: not read) the ascending list of the
+    entries to send and how many of them belong to my first half (they are sent, and flagged, first)."""
+    lst = np.flatnonzero(np.asarray(slots_at_destination) >= 0)
+    return lst, int(np.searchsorted(lst, half))

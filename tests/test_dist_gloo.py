@@ -177,3 +177,77 @@ def test_slice_bounds_tile_the_columns():
         assert b[0][0] == 0 and b[-1][1] == n
         assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
         assert all(0 <= hi - lo <= nslice for lo, hi in b)
+
+
+def _packed_worker(rank, world, port, q):
+    """The packed exchange end to end with gloo as the wire: every rank marks the columns its rows of A touch, numbers them in
+    two halves, learns from every peer where its own entries live in the peer's packed buffer, sends first halves then second
+    halves — and its renumbered matrix times the packed buffer must equal A_g times the full vector."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lp = lpgen.sparse_lp(3000, 2500, 2, seed=5)  # 2 entries per row: a rank reads well under all of the columns
+        A = sp.csr_matrix((lp.values, lp.indices, lp.offsets), shape=(lp.m, lp.n))
+        b = cdist.shard_bounds(lp.offsets, world)
+        Ag = A[int(b[rank]):int(b[rank + 1])].tocsr()
+        nslice, bounds = cdist.slice_bounds(lp.n, world)
+        n_pad = nslice * world
+        starts = np.arange(world + 1) * nslice
+        halves = np.full(world, nslice // 2)
+        needed = np.zeros(n_pad, bool)
+        needed[Ag.indices] = True
+        pos, W = cdist.packed_layout(needed, starts, halves)
+        assert 0.2 < needed[:lp.n].mean() < 0.95  # the packing has something to skip
+        # every rank learns every peer's slot table
+        tables = [torch.zeros(n_pad, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(tables, torch.from_numpy(pos))
+        widths = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(widths, torch.tensor([W]))
+        j0 = rank * nslice
+        rng = np.random.default_rng(100)
+        x_full = rng.standard_normal(n_pad)  # same on every rank; rank h "produces" x_full[h * nslice:(h + 1) * nslice]
+        x_mine = x_full[j0:j0 + nslice]
+        # what I send to destination r: (slots, values), first-half entries first
+        outgoing = []
+        for r in range(world):
+            slots = tables[r].numpy()[j0:j0 + nslice]
+            lst, count_a = cdist.send_list(slots, nslice // 2)
+            assert np.all(np.diff(slots[lst][:count_a]) == 1) and np.all(np.diff(slots[lst][count_a:]) == 1)  # consecutive per half
+            assert np.all(slots[lst][:count_a] < int(widths[r])) and np.all(slots[lst][count_a:] >= int(widths[r]))
+            outgoing.append((slots[lst], x_mine[lst], count_a))
+        # the wire: gather everybody's messages for me (gloo: all_gather of padded arrays)
+        buf = np.full(2 * W, np.nan)
+        for src in range(world):
+            for dst in range(world):
+                sl, va, _ = outgoing[dst] if src == rank else (np.zeros(0, np.int64), np.zeros(0), 0)
+                n_msg = torch.tensor([len(sl)])
+                dist.broadcast(n_msg, src=src)
+                t_sl = torch.from_numpy(sl.astype(np.int64)) if src == rank else torch.zeros(int(n_msg), dtype=torch.int64)
+                t_va = torch.from_numpy(va.copy()) if src == rank else torch.zeros(int(n_msg), dtype=torch.float64)
+                dist.broadcast(t_sl, src=src)
+                dist.broadcast(t_va, src=src)
+                if dst == rank:
+                    buf[t_sl.numpy()] = t_va.numpy()
+        remapped = sp.csr_matrix((Ag.data, pos[Ag.indices], Ag.indptr), shape=(Ag.shape[0], 2 * W))
+        assert not np.isnan(buf[pos[needed]]).any()
+        ok = np.allclose(remapped @ np.nan_to_num(buf), Ag @ x_full[:lp.n], rtol=1e-13, atol=1e-13)
+        # block 0 of the column split (slots < W) touches first halves only
+        first_half_cols = (np.arange(n_pad) % nslice) < nslice // 2
+        ok = ok and bool(np.all(first_half_cols[np.flatnonzero(needed)][pos[needed] < W]))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_packed_exchange_delivers_what_each_rank_reads(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_packed_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(60)
+    assert all(r[1] for r in res), res
