@@ -20,7 +20,6 @@ constexpr int WARP_THREADS = 256;                // CTA size of the warp-block k
 constexpr int WARP_PER_CTA = WARP_THREADS / 32;
 constexpr int WARP_NNZ     = 256;                // nonzeros per warp block (8 per lane)
 constexpr int WARP_KN      = WARP_NNZ / 32;
-constexpr int WARP_WIDE_RPL = 8;                 // rows per lane of the wide schedule (blocks of <= 256 rows)
 __host__ __device__ constexpr int warp_swz(int e) { return e ^ ((e >> 4) & 7); }
 
 struct csr_warp_view_t {
