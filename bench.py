@@ -401,6 +401,16 @@ def main():
                 "peak_source": peak_kind, "algorithmic_bytes_per_launch": by, "ms_per_launch": ms,
                 "measured_on": "1 GPU, the full LP" + ("" if world == 1 else
                                f" (a probe on rank 0's GPU beside the {world}-GPU run: the sharded attempt runs other kernels on 1/{world} of the rows; see detail.kernels)")}
+        # second bound of the SpMV steps (profiles/r2/request_port_roofline.md): every gathered double of a random column is one
+        # L1TEX miss request and an SM sends at most one request per clock towards L2
+        try:
+            sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+            sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
+            floor_ms = 1e3 * (lp.nnz + (12 * lp.nnz) / 128.0) / (sm_count * sm_hz)  # gathers + coalesced 128-byte stream requests
+            roof["request_port"] = {"what": "L1TEX -> crossbar requests: 1 per clock per SM; one per gathered double + one per 128 B of matrix stream",
+                                    "floor_ms_per_launch": floor_ms, "frac_of_floor": floor_ms / ms if dom != "k_primal_step" else None}
+        except Exception:  # noqa: BLE001
+            pass
         b_iter = lp.algorithmic_bytes_per_iteration()
         extra = {"kernels": {k: {"ms": v[0], "algorithmic_GBps": v[1] / (v[0] * 1e-3) / 1e9} for k, v in ks.items()},
                  "iteration": {"ms_in_batch": prof.ms_iteration, "algorithmic_bytes": b_iter,
