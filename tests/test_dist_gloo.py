@@ -7,6 +7,9 @@
     of three scalars per rank) reproduces the same attempt and the same bits on every rank,
   * the gather transport (rows of A and rows of the global A^T per rank, xbar and y' all-gathered, no partial products)
     reproduces the same attempt, and its slice of A^T assembled from the transposed row blocks equals the real one,
+  * twenty accepted steps of the gather transport with the adaptive step-size rule on the rank-ordered scalars follow the
+    oracle's own twenty steps (same accept / reject decisions on every rank, iterates to 1e-10),
+  * the packed exchange (two halves, slot tables, send lists) delivers exactly what every rank reads,
   * the slice bounds tile [0, n) with 32-aligned slices.
 The CUDA side of the same protocols is exercised by tests/test_gpu_dist.py on >= 2 GPUs."""
 import os
@@ -251,3 +254,88 @@ def test_packed_exchange_delivers_what_each_rank_reads(world):
     for p in procs:
         p.join(60)
     assert all(r[1] for r in res), res
+
+
+def _trajectory_worker(rank, world, port, q):
+    """20 accepted PDHG steps of the gather transport (numpy + gloo), with the adaptive step-size rule evaluated on the three
+    rank-ordered scalars, against the oracle's own 20 steps from the same state: same accept / reject decisions, same
+    iterates.  Started after 12 iterations (the every-iteration major iterations of k <= 10 are over, the next one is at 40)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lp = lpgen.sparse_lp(3000, 2500, 6, seed=11)
+        o = po.Oracle(lp.offsets, lp.indices, lp.values, lp.c, lp.var_lb, lp.var_ub, lp.con_lb, lp.con_ub)
+        o.run(12)
+        x, y, aty = o.vector("x"), o.vector("y"), o.vector("aty")
+        eta, w, kp = o.scalar("step_size"), o.scalar("primal_weight"), int(o.scalar("k_pdhg"))
+        dr, dc = o.vector("row_scaling"), o.vector("col_scaling")
+        A = sp.csr_matrix((lp.values, lp.indices, lp.offsets), shape=(lp.m, lp.n))
+        As = (sp.diags(dr) @ A @ sp.diags(dc)).tocsr()
+        cs, ls, us = o.vector("scaled_c"), o.vector("scaled_l"), o.vector("scaled_u")
+        lcs, ucs = o.vector("scaled_lc"), o.vector("scaled_uc")
+        b = cdist.shard_bounds(lp.offsets, world)
+        r0, r1 = int(b[rank]), int(b[rank + 1])
+        nslice, bounds = cdist.slice_bounds(lp.n, world)
+        j0, j1 = bounds[rank]
+        Ag = As[r0:r1].tocsr()
+        at_slice = As.T.tocsr()[j0:j1]
+
+        def allgather(buf):
+            g = [torch.zeros(len(buf), dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(g, torch.from_numpy(buf.copy()))
+            return torch.cat(g).numpy()
+
+        def allgather_y(v):
+            sizes = [int(b[g + 1] - b[g]) for g in range(world)]
+            pad = np.zeros(max(sizes)); pad[: len(v)] = v
+            g = [torch.zeros(max(sizes), dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(g, torch.from_numpy(pad))
+            return np.concatenate([g[k].numpy()[: sizes[k]] for k in range(world)])
+
+        def allgather_scalars(v):
+            g = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(g, torch.from_numpy(v.copy()))
+            return torch.stack(g).numpy()
+
+        xs, ys, ats = x[j0:j1].copy(), y[r0:r1].copy(), aty[j0:j1].copy()
+        accepted = attempts = 0
+        while accepted < 20 and attempts < 200:
+            attempts += 1
+            tau, sigma = eta / w, eta * w
+            xn = np.maximum(np.minimum(xs - tau * (cs[j0:j1] - ats), us[j0:j1]), ls[j0:j1])
+            yn, atn, inter, dx2, dy2 = cdist.reference_protocol_step_gather(
+                Ag, at_slice, rank, world, xs, xn, ats, ys, sigma, lcs[r0:r1], ucs[r0:r1], allgather, allgather_y,
+                allgather_scalars)
+            # adaptive_step_size_strategy.cu:92-188 (pdhg_step_rule in pdlp_kernels.cuh), on the rank-ordered sums
+            movement = 0.5 * w * dx2 + (0.5 / w) * dy2
+            assert 0.0 < movement < 1e100
+            kp += 1
+            limit = movement / abs(inter) if inter != 0.0 else np.inf
+            accept = eta <= limit
+            eta = min((1.0 - (kp + 1.0) ** -0.3) * limit, (1.0 + (kp + 1.0) ** -0.6) * eta)
+            if accept:
+                xs, ys, ats = xn, yn, atn
+                accepted += 1
+        o.run(20)
+        ox, oy = o.vector("x"), o.vector("y")
+        ok = (accepted == 20 and kp == int(o.scalar("k_pdhg"))
+              and np.allclose(xs, ox[j0:j1], rtol=1e-10, atol=1e-11) and np.allclose(ys, oy[r0:r1], rtol=1e-10, atol=1e-11)
+              and abs(eta - o.scalar("step_size")) <= 1e-10 * eta)
+        q.put((rank, bool(ok), attempts))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_transport_follows_the_oracle_over_twenty_steps(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_trajectory_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(60)
+    assert all(r[1] for r in res), res
+    assert len({r[2] for r in res}) == 1  # every rank took the same number of attempts (identical accept / reject decisions)
