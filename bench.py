@@ -263,7 +263,7 @@ def main():
                     help="iteration cap of the untimed time-to-1e-6-gap solve reported in detail (0 = skip)")
     ap.add_argument("--gap-time-limit", type=float, default=150.0, help="time cap (s) of that solve")
     ap.add_argument("--profile-reps", type=int, default=200)
-    ap.add_argument("--simplex-cap", type=float, default=40.0,
+    ap.add_argument("--simplex-cap", type=float, default=20.0,
                     help="seconds given to the reference's own CPU path (dual simplex, 1 core) on this LP; 0 = skip")
     ap.add_argument("--comparator", default="auto", choices=["auto", "off"],
                     help="time the cuSPARSE/cuBLAS re-assembly of the reference's attempt (scripts/cusparse_pdhg.cu) beside ours")
